@@ -1,0 +1,272 @@
+// Exact-float32 dense 1-D convolution on CUDA cores (the parity mode, BC_PREC_FP32).
+//
+// One kernel covers every dense contraction of the path (SURVEY.md section 8 rows a3-a5,
+// a10-a11): dilated k7 "same" convs, 1x1 convs, strided down convs (k = 2s), the
+// 2-tap phase convs a transposed conv decomposes into, the 1->C and C->1 edge convs and
+// the LSTM input projection (k = 1).  SnakeBeta is applied while the input slab is
+// staged (so the activation never makes an HBM round trip), bias / residual / tanh in
+// the epilogue.
+//
+// Tiling: CTA = 128 output steps x BN output channels, 128 threads, each thread an
+// 8 x (BN/8) register tile; input channels are consumed in chunks of 16 through a
+// shared-memory slab holding every input row the tile's taps touch.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;     // output time steps per CTA
+constexpr int CK = 16;      // input-channel chunk
+constexpr int CKP = CK + 1; // padded slab row (bank-conflict-free column reads)
+constexpr int NTHREADS = 128;
+
+struct ConvParams {
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* sa;
+  const float* sib;
+  const float* res;
+  float* y;
+  int B, T_in, C_in, T_out, C_out, K, stride, dil, pad_left;
+  int y_rows, y_tstride, y_toffset, flags;
+  int slab_rows;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) conv1d_f32_kernel(const ConvParams p) {
+  constexpr int TN = BN / 8;  // output channels per thread
+  extern __shared__ __align__(16) float smem[];
+  float* slab = smem;                          // [slab_rows][CKP]
+  float* ws = smem + (size_t)p.slab_rows * CKP; // [K][CK][BN]
+  // keep ws 16-byte aligned
+  ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~uintptr_t(15));
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+  const float* xb = p.x + (size_t)b * p.T_in * p.C_in;
+  const int g0 = t0 * p.stride - p.pad_left;  // global input row of slab row 0
+  const bool snake = (p.flags & BC_CONV_SNAKE_IN) != 0;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  int arow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) arow[i] = (ty + 16 * i) * p.stride * CKP;
+
+  const bool vec_x = (p.C_in % 4 == 0) && bc::aligned16(p.x);
+  const bool vec_w = (p.C_out % 4 == 0) && bc::aligned16(p.w);
+
+  for (int ci0 = 0; ci0 < p.C_in; ci0 += CK) {
+    __syncthreads();  // previous chunk fully consumed
+    // ---- stage the input slab (activation fused) ----
+    if (vec_x) {
+      const int c4 = (tid & 3) * 4;
+      const int ci = ci0 + c4;
+      const bool cok = ci < p.C_in;  // C_in % 4 == 0 => whole float4 in range
+      float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (snake && cok) {
+        a4 = __ldg(reinterpret_cast<const float4*>(p.sa + ci));
+        b4 = __ldg(reinterpret_cast<const float4*>(p.sib + ci));
+      }
+      for (int r = tid >> 2; r < p.slab_rows; r += NTHREADS / 4) {
+        const int g = g0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cok && g >= 0 && g < p.T_in) {
+          v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)g * p.C_in + ci));
+          if (snake) {
+            v.x = bc::snake_ref(v.x, a4.x, b4.x);
+            v.y = bc::snake_ref(v.y, a4.y, b4.y);
+            v.z = bc::snake_ref(v.z, a4.z, b4.z);
+            v.w = bc::snake_ref(v.w, a4.w, b4.w);
+          }
+        }
+        float* d = slab + r * CKP + c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      const int c = tid & 15;
+      const int ci = ci0 + c;
+      const bool cok = ci < p.C_in;
+      float a = 1.f, ib = 0.f;
+      if (snake && cok) { a = __ldg(p.sa + ci); ib = __ldg(p.sib + ci); }
+      for (int r = tid >> 4; r < p.slab_rows; r += NTHREADS / 16) {
+        const int g = g0 + r;
+        float v = 0.f;
+        if (cok && g >= 0 && g < p.T_in) {
+          v = __ldg(xb + (size_t)g * p.C_in + ci);
+          if (snake) v = bc::snake_ref(v, a, ib);
+        }
+        slab[r * CKP + c] = v;
+      }
+    }
+    // ---- stage the weight tile w[k][ci0+c][co0+n] ----
+    if (vec_w) {
+      constexpr int N4 = BN / 4;
+      const int total = p.K * CK * N4;
+      for (int e = tid; e < total; e += NTHREADS) {
+        const int n4 = e % N4;
+        const int kc = e / N4;
+        const int c = kc % CK, k = kc / CK;
+        const int ci = ci0 + c, co = co0 + n4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ci < p.C_in && co < p.C_out)
+          v = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)k * p.C_in + ci) * p.C_out + co));
+        *reinterpret_cast<float4*>(ws + (size_t)kc * BN + n4 * 4) = v;
+      }
+    } else {
+      const int total = p.K * CK * BN;
+      for (int e = tid; e < total; e += NTHREADS) {
+        const int n = e % BN;
+        const int kc = e / BN;
+        const int c = kc % CK, k = kc / CK;
+        const int ci = ci0 + c, co = co0 + n;
+        float v = 0.f;
+        if (ci < p.C_in && co < p.C_out) v = __ldg(p.w + ((size_t)k * p.C_in + ci) * p.C_out + co);
+        ws[(size_t)kc * BN + n] = v;
+      }
+    }
+    __syncthreads();
+
+    // ---- FFMA main loop ----
+    for (int k = 0; k < p.K; ++k) {
+      const float* sx = slab + k * p.dil * CKP;
+      const float* sw = ws + (size_t)k * CK * BN + tx * 4;
+#pragma unroll
+      for (int c = 0; c < CK; ++c) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = sx[arow[i] + c];
+        float bv[TN];
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(sw + c * BN + (j >> 2) * 32);
+          bv[j] = t4.x; bv[j + 1] = t4.y; bv[j + 2] = t4.z; bv[j + 3] = t4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+      }
+    }
+  }
+
+  // ---- epilogue: bias, residual, tanh, store ----
+  // thread's channel j lives at column (j/4)*32 + tx*4 + j%4 of the tile (conflict-free
+  // float4 smem reads above, 128-byte contiguous row segments per 8 lanes here)
+  const bool tanh_out = (p.flags & BC_CONV_TANH_OUT) != 0;
+  const bool vec_ok = (p.C_out % 4 == 0) && bc::aligned16(p.y) && (!p.res || bc::aligned16(p.res));
+#pragma unroll
+  for (int jg = 0; jg < TN / 4; ++jg) {
+    const int co = co0 + jg * 32 + tx * 4;
+    if (co >= p.C_out) continue;
+    float bias[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bias[e] = (p.bias && co + e < p.C_out) ? __ldg(p.bias + co + e) : 0.f;
+    const bool vec_y = vec_ok && (co + 4 <= p.C_out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + ty + 16 * i;
+      if (t >= p.T_out) continue;
+      const size_t row = (size_t)b * p.y_rows + (size_t)t * p.y_tstride + p.y_toffset;
+      float* yp = p.y + row * p.C_out + co;
+      const float* rp = p.res ? p.res + row * p.C_out + co : nullptr;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = acc[i][jg * 4 + e] + bias[e];
+      if (vec_y) {
+        if (rp) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp);
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        if (tanh_out) { v[0] = tanhf(v[0]); v[1] = tanhf(v[1]); v[2] = tanhf(v[2]); v[3] = tanhf(v[3]); }
+        *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (co + e < p.C_out) {
+            float o = v[e];
+            if (rp) o += rp[e];
+            if (tanh_out) o = tanhf(o);
+            yp[e] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BN>
+int launch(const ConvParams& p, cudaStream_t st) {
+  const size_t smem = ((size_t)p.slab_rows * CKP + (size_t)p.K * CK * BN) * sizeof(float) + 16;
+  if (smem > 227 * 1024) return bc::fail(BC_EUNSUPPORTED, "conv1d(fp32): tile needs %zu B of shared memory (K=%d stride=%d dil=%d)", smem, p.K, p.stride, p.dil);
+  if (smem > 48 * 1024) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(conv1d_f32)");
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+  }
+  dim3 grid((p.T_out + BM - 1) / BM, (p.C_out + BN - 1) / BN, p.B);
+  conv1d_f32_kernel<BN><<<grid, NTHREADS, smem, st>>>(p);
+  BC_LAUNCH_CHECK("conv1d_f32_kernel");
+  return BC_OK;
+}
+
+}  // namespace
+
+namespace bc {
+int conv1d_tc_fwd(const float* x, const float* w, const float* bias, const float* snake_a, const float* snake_ib,
+                  const float* res, float* y, int B, int T_in, int C_in, int T_out, int C_out, int K, int stride,
+                  int dilation, int pad_left, int y_rows, int y_tstride, int y_toffset, int flags, int precision,
+                  cudaStream_t st);
+}
+
+extern "C" int bc_conv1d_fwd(const float* x, const float* w, const float* bias, const float* snake_a,
+                             const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                             int C_out, int K, int stride, int dilation, int pad_left, int y_rows, int y_tstride,
+                             int y_toffset, int flags, int precision, bc_stream_t s) {
+  BC_REQUIRE(x && w && y, "conv1d: null pointer");
+  BC_REQUIRE(B > 0 && T_in > 0 && C_in > 0 && T_out > 0 && C_out > 0, "conv1d: bad shape B=%d T_in=%d C_in=%d T_out=%d C_out=%d", B, T_in, C_in, T_out, C_out);
+  BC_REQUIRE(K > 0 && K <= 64 && stride > 0 && dilation > 0, "conv1d: bad K=%d stride=%d dilation=%d", K, stride, dilation);
+  BC_REQUIRE(y_tstride > 0 && y_toffset >= 0 && y_rows >= (T_out - 1) * y_tstride + y_toffset + 1, "conv1d: output geometry y_rows=%d tstride=%d toffset=%d T_out=%d", y_rows, y_tstride, y_toffset, T_out);
+  BC_REQUIRE(B <= 65535, "conv1d: B=%d > 65535 (split the batch)", B);
+  if (flags & BC_CONV_SNAKE_IN) BC_REQUIRE(snake_a && snake_ib, "conv1d: BC_CONV_SNAKE_IN without snake parameters");
+  if (precision != BC_PREC_FP32)
+    return bc::conv1d_tc_fwd(x, w, bias, snake_a, snake_ib, res, y, B, T_in, C_in, T_out, C_out, K, stride, dilation,
+                             pad_left, y_rows, y_tstride, y_toffset, flags, precision, (cudaStream_t)s);
+  ConvParams p;
+  p.x = x; p.w = w; p.bias = bias; p.sa = snake_a; p.sib = snake_ib; p.res = res; p.y = y;
+  p.B = B; p.T_in = T_in; p.C_in = C_in; p.T_out = T_out; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;
+  p.pad_left = pad_left; p.y_rows = y_rows; p.y_tstride = y_tstride; p.y_toffset = y_toffset; p.flags = flags;
+  p.slab_rows = (BM - 1) * stride + (K - 1) * dilation + 1;
+  if (C_out > 32) return launch<64>(p, (cudaStream_t)s);
+  return launch<32>(p, (cudaStream_t)s);
+}
+
+extern "C" int bc_convtr1d_fwd(const float* x, const float* w_phases, const float* bias, const float* snake_a,
+                               const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                               int padding, int flags, int precision, bc_stream_t s) {
+  BC_REQUIRE(x && w_phases && y, "convtr1d: null pointer");
+  BC_REQUIRE(stride >= 2 && padding >= 0 && padding < stride, "convtr1d: stride=%d padding=%d (need stride >= 2, 0 <= padding < stride)", stride, padding);
+  const int T_out = T_in * stride;
+  for (int ph = 0; ph < stride; ++ph) {
+    const int q = (ph + padding) / stride;  // 0 or 1
+    // y[m*stride + ph] = W[j0+stride]^T x[m+q-1] + W[j0]^T x[m+q]
+    const float* wp = w_phases + (size_t)ph * 2 * C_in * C_out;
+    int rc = bc_conv1d_fwd(x, wp, bias, snake_a, snake_ib, nullptr, y, B, T_in, C_in, T_in, C_out, /*K=*/2,
+                           /*stride=*/1, /*dil=*/1, /*pad_left=*/1 - q, /*y_rows=*/T_out, /*y_tstride=*/stride,
+                           /*y_toffset=*/ph, flags, precision, s);
+    if (rc != BC_OK) return rc;
+  }
+  return BC_OK;
+}

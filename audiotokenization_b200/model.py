@@ -1,0 +1,136 @@
+"""Driver-level wrapper: the ``BigCodecModel`` of extract_indices.py / inference_full.py.
+
+``forward`` keeps the reference wrappers' call pattern and result dicts
+(extract_indices.py:347-371, inference_full.py:557-561) with the semantic mapping
+``lm.model['CodecEnc'] == encoder`` and ``lm.model['generator'] == decoder``
+(SURVEY.md section 0).  ``extract_indices`` is the batched host-buffer entry point the
+benchmark's end-to-end number goes through: pinned host waveforms in, int16 ``(T', n_q)``
+index arrays out (the on-disk layout of extract_indices.py:520-532).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi, configs, ops
+from .vq import BigCodecDecoder, BigCodecEncoder, set_precision
+
+
+def _strip_prefix(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+class BigCodecModel(nn.Module):
+    def __init__(self, cfg: dict, enc_state: Optional[dict] = None, dec_state: Optional[dict] = None,
+                 device: str = "cuda", precision: str = "fp32"):
+        super().__init__()
+        _cabi.load_library()  # fail loudly before anything else if the CUDA library is missing
+        self.cfg = cfg
+        self.encoder = BigCodecEncoder(**cfg["codec_encoder"])
+        self.decoder = BigCodecDecoder(**cfg["codec_decoder"])
+        if enc_state is not None:
+            self.encoder.load_state_dict(enc_state, strict=True)
+        if dec_state is not None:
+            self.decoder.load_state_dict(dec_state, strict=True)
+        self.codebook_size = cfg["codec_decoder"]["codebook_size"]
+        self.precision = precision
+        self.to(device)
+        self.eval()
+
+    # -- checkpoint adapter (extract_indices.py:309-323) ---------------------------------
+    @classmethod
+    def from_checkpoint(cls, ckpt_path: str, config_path: str, device: str = "cuda", precision: str = "fp32"):
+        cfg = configs.load_model_yaml(config_path)
+        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        sd = ckpt.get("state_dict", ckpt.get("model", ckpt)) if isinstance(ckpt, dict) else ckpt
+        enc = _strip_prefix(sd, "encoder.") or _strip_prefix(sd, "model.CodecEnc.")
+        dec = _strip_prefix(sd, "decoder.") or _strip_prefix(sd, "model.generator.")
+        m = cls(cfg, device=device, precision=precision)
+        try:
+            m.encoder.load_state_dict(enc, strict=True)
+            m.decoder.load_state_dict(dec, strict=True)
+        except RuntimeError as e:  # the reference falls back to non-strict loading (extract_indices.py:318-323)
+            print(f"Strict state_dict loading failed: {e}. Attempting non-strict loading.")
+            m.encoder.load_state_dict(enc, strict=False)
+            m.decoder.load_state_dict(dec, strict=False)
+        return m
+
+    # -- reference call pattern ---------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, round_trip: bool = False):
+        """x [B,1,T] on the GPU.  ``{'indices'}`` (extract_indices) or, with ``round_trip``,
+        ``{'x_rec','indices','loss'}`` (inference_full)."""
+        set_precision(self.precision)
+        vq_emb = self.encoder(x)
+        vq_post_emb, vq_code, _ = self.decoder(vq_emb, vq=True)
+        if not round_trip:
+            return {"indices": vq_code}
+        recon = self.decoder(vq_post_emb, vq=False)
+        return {"x_rec": recon, "indices": vq_code, "loss": {}}
+
+    @torch.no_grad()
+    def inference(self, wav: torch.Tensor) -> torch.Tensor:
+        """CodecLightningModule.inference (lightning_module.py:280-285): wav [B,T] -> recon [B,T]."""
+        return self.forward(wav.unsqueeze(1), round_trip=True)["x_rec"].squeeze(1)
+
+    # -- device-resident fast path ---------------------------------------------------------------
+    @torch.no_grad()
+    def encode_indices_cl(self, x_cl: torch.Tensor, want_margin: bool = False):
+        """x_cl [B,T,1] device -> (idx int32 [n_q,B,T'], margin [n_q,B,T'] | None, z_cl [B,T',C])."""
+        set_precision(self.precision)
+        z_cl = self.encoder.forward_cl(x_cl)
+        _, idx, margin = self.decoder.quantizer.forward_cl(z_cl, want_margin=want_margin)
+        return idx, margin, z_cl
+
+    @torch.no_grad()
+    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8) -> torch.Tensor:
+        """Device waveforms [N,1,T] -> int16 [N,T',n_q] on the device, micro-batched."""
+        outs = []
+        for b0 in range(0, x_dev.shape[0], micro_batch):
+            xb = x_dev[b0:b0 + micro_batch]
+            idx, _, _ = self.encode_indices_cl(xb.reshape(xb.shape[0], xb.shape[2], 1))
+            n_q, B, Tp = idx.shape
+            outs.append(ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q))
+        return torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8) -> np.ndarray:
+        """Host (ideally pinned) float32 waveforms [N,1,T] -> int16 numpy [N,T',n_q].
+
+        Each micro-batch is copied H2D on a side stream while the previous one computes;
+        results come back D2H as int16.  Equal-length clips only (ragged batches are not
+        equivalent to the reference's per-utterance padding)."""
+        if wave_host.is_cuda:
+            raise ValueError("extract_indices takes HOST waveforms; use indices_device for device tensors")
+        dev = next(self.parameters()).device
+        N = wave_host.shape[0]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        results = []
+        nxt = None
+
+        def stage(b0):
+            with torch.cuda.stream(copy_stream):
+                t = wave_host[b0:b0 + micro_batch].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return t, ev
+
+        nxt = stage(0)
+        for b0 in range(0, N, micro_batch):
+            xb, ev = nxt
+            main.wait_event(ev)
+            xb.record_stream(main)
+            if b0 + micro_batch < N:
+                nxt = stage(b0 + micro_batch)
+            idx, _, _ = self.encode_indices_cl(xb.reshape(xb.shape[0], xb.shape[2], 1))
+            n_q, B, Tp = idx.shape
+            i16 = ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
+            host = torch.empty(i16.shape, dtype=torch.int16, pin_memory=True)
+            host.copy_(i16, non_blocking=True)
+            results.append(host)
+        torch.cuda.current_stream(dev).synchronize()
+        return np.concatenate([r.numpy() for r in results], axis=0)

@@ -1,0 +1,214 @@
+"""Host-side operator layer: thin, shape-checked wrappers over the C ABI.
+
+All activations here are float32 CUDA tensors in CHANNELS-LAST layout ``[B, T, C]``
+(contiguous).  Each function allocates its output with torch (device memory is
+torch's job), passes raw pointers to the library on the current stream and returns
+the output tensor.  No arithmetic happens in Python.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import BC_CONV_SNAKE_IN, BC_CONV_TANH_OUT, PRECISIONS, check, load_library, ptr, require_cuda, stream_ptr
+
+
+# launch accounting (bench.py's ``gpu_launches``) and optional per-call event timing of the
+# dense contractions (bench.py's roofline leg).  PROFILE is None or a list that receives
+# (kind, flops, start_event, end_event) per conv call.
+STATS = {"launches": 0}
+PROFILE = None
+
+
+def _count(n: int = 1) -> None:
+    STATS["launches"] += n
+
+
+class _Timed:
+    def __init__(self, kind, flops, device):
+        self.kind, self.flops, self.device = kind, flops, device
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream(self.device))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
+def _cl(x: torch.Tensor, name="x") -> torch.Tensor:
+    require_cuda(x, name)
+    if x.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {x.dtype}")
+    if x.dim() != 3:
+        raise ValueError(f"{name} must be [B,T,C], got {tuple(x.shape)}")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def to_channels_last(x_bct: torch.Tensor) -> torch.Tensor:
+    """[B,C,T] (any strides) -> contiguous [B,T,C]."""
+    require_cuda(x_bct, "x")
+    if x_bct.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {x_bct.dtype}")
+    B, C, T = x_bct.shape
+    v = x_bct.permute(0, 2, 1)
+    if v.is_contiguous():          # already channels-last storage (or C == 1)
+        return v
+    x_bct = x_bct.contiguous()
+    y = torch.empty((B, T, C), device=x_bct.device, dtype=torch.float32)
+    check(load_library().bc_transpose_bct_to_btc(ptr(x_bct), ptr(y), B, C, T, stream_ptr(x_bct.device)),
+          "bc_transpose_bct_to_btc")
+    _count()
+    return y
+
+
+def to_channels_first(x_btc: torch.Tensor) -> torch.Tensor:
+    """contiguous [B,T,C] -> contiguous [B,C,T]."""
+    x_btc = _cl(x_btc)
+    B, T, C = x_btc.shape
+    if C == 1 or T == 1:
+        return x_btc.reshape(B, C, T)
+    y = torch.empty((B, C, T), device=x_btc.device, dtype=torch.float32)
+    check(load_library().bc_transpose_btc_to_bct(ptr(x_btc), ptr(y), B, T, C, stream_ptr(x_btc.device)),
+          "bc_transpose_btc_to_bct")
+    _count()
+    return y
+
+
+def snake(x: torch.Tensor, a: torch.Tensor, ib: torch.Tensor, antialias: bool = False,
+          fir: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SnakeBeta / anti-aliased Activation1d on a channels-last tensor."""
+    x = _cl(x)
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    check(load_library().bc_snake_fwd(ptr(x), ptr(y), ptr(a), ptr(ib), ptr(fir) if antialias else None,
+                                      B, T, C, int(bool(antialias)), stream_ptr(x.device)), "bc_snake_fwd")
+    _count()
+    return y
+
+
+def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int = 1, dilation: int = 1,
+           pad_left: int = 0, t_out: int, snake_a: Optional[torch.Tensor] = None,
+           snake_ib: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, tanh: bool = False,
+           precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dense conv, weights packed ``[K, C_in, C_out]``; see bc_conv1d_fwd."""
+    x = _cl(x)
+    B, T_in, C_in = x.shape
+    K, wc_in, C_out = w.shape
+    if wc_in != C_in:
+        raise ValueError(f"conv1d: input has {C_in} channels, weight expects {wc_in}")
+    if t_out <= 0:
+        raise ValueError(f"conv1d: input of {T_in} steps is too short for this layer (T_out={t_out})")
+    y = out if out is not None else torch.empty((B, t_out, C_out), device=x.device, dtype=torch.float32)
+    flags = (BC_CONV_SNAKE_IN if snake_a is not None else 0) | (BC_CONV_TANH_OUT if tanh else 0)
+    if res is not None:
+        res = _cl(res, "res")
+        if tuple(res.shape) != (B, t_out, C_out):
+            raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, C_out)}")
+    with _Timed("conv1d", 2.0 * B * t_out * C_out * C_in * K, x.device):
+        check(load_library().bc_conv1d_fwd(ptr(x), ptr(w), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res), ptr(y),
+                                           B, T_in, C_in, t_out, C_out, K, stride, dilation, pad_left,
+                                           t_out, 1, 0, flags, PRECISIONS[precision], stream_ptr(x.device)),
+              "bc_conv1d_fwd")
+    _count()
+    return y
+
+
+def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int,
+                     padding: int, snake_a: Optional[torch.Tensor] = None, snake_ib: Optional[torch.Tensor] = None,
+                     precision: str = "fp32") -> torch.Tensor:
+    """Transposed conv (k = 2*stride) from phase-packed weights ``[stride, 2, C_in, C_out]``."""
+    x = _cl(x)
+    B, T_in, C_in = x.shape
+    s, two, wc_in, C_out = w_phases.shape
+    if s != stride or two != 2 or wc_in != C_in:
+        raise ValueError(f"conv_transpose1d: weight {tuple(w_phases.shape)} does not match stride={stride}, C_in={C_in}")
+    y = torch.empty((B, T_in * stride, C_out), device=x.device, dtype=torch.float32)
+    flags = BC_CONV_SNAKE_IN if snake_a is not None else 0
+    with _Timed("convtr1d", 2.0 * B * T_in * stride * C_out * C_in * 2, x.device):
+        check(load_library().bc_convtr1d_fwd(ptr(x), ptr(w_phases), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(y),
+                                             B, T_in, C_in, C_out, stride, padding, flags, PRECISIONS[precision],
+                                             stream_ptr(x.device)), "bc_convtr1d_fwd")
+    _count(stride)
+    return y
+
+
+LSTM_MAX_BATCH = 256
+
+
+def lstm_recurrent(pre: torch.Tensor, w_hh_packed: torch.Tensor, skip: Optional[torch.Tensor]) -> torch.Tensor:
+    """Recurrent part of one LSTM layer; ``pre`` = [B,T,4H] input projection (+ both biases)."""
+    pre = _cl(pre, "pre")
+    B, T, H4 = pre.shape
+    H = H4 // 4
+    lib = load_library()
+    y = torch.empty((B, T, H), device=pre.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _cl(skip, "skip")
+    for b0 in range(0, B, LSTM_MAX_BATCH):
+        b1 = min(B, b0 + LSTM_MAX_BATCH)
+        ws = torch.empty(lib.bc_lstm_workspace_bytes(b1 - b0, H), device=pre.device, dtype=torch.uint8)
+        with _Timed("lstm", 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
+            check(lib.bc_lstm_recurrent_fwd(ptr(pre[b0:b1]), ptr(w_hh_packed),
+                                            ptr(skip[b0:b1]) if skip is not None else None,
+                                            ptr(y[b0:b1]), ptr(ws), b1 - b0, T, H, stream_ptr(pre.device)),
+                  "bc_lstm_recurrent_fwd")
+        _count()
+    return y
+
+
+def vq_encode(z: torch.Tensor, w_in: Optional[torch.Tensor], b_in: Optional[torch.Tensor], cb_norm: torch.Tensor,
+              want_margin: bool = False, want_ze: bool = False):
+    """z [N,C] -> (idx int32 [N], margin [N] | None, z_e [N,D] | None)."""
+    require_cuda(z, "z")
+    z = z if z.is_contiguous() else z.contiguous()
+    N, C = z.shape
+    Kc, D = cb_norm.shape
+    idx = torch.empty((N,), device=z.device, dtype=torch.int32)
+    margin = torch.empty((N,), device=z.device, dtype=torch.float32) if want_margin else None
+    z_e = torch.empty((N, D), device=z.device, dtype=torch.float32) if want_ze else None
+    check(load_library().bc_vq_encode(ptr(z), ptr(w_in), ptr(b_in), ptr(cb_norm), ptr(idx), ptr(margin), ptr(z_e),
+                                      N, C, D, Kc, stream_ptr(z.device)), "bc_vq_encode")
+    _count()
+    return idx, margin, z_e
+
+
+def vq_dequant(idx: torch.Tensor, cb: torch.Tensor, w_out: Optional[torch.Tensor], b_out: Optional[torch.Tensor],
+               C: int, *, z_q: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+               check_range: bool = True) -> torch.Tensor:
+    """idx int32 [N] -> z_q [N,C] (accumulating into ``z_q`` when given; ``residual -= q``)."""
+    require_cuda(idx, "idx")
+    if idx.dtype != torch.int32:
+        idx = idx.to(torch.int32)
+    idx = idx.contiguous()
+    N = idx.numel()
+    Kc, D = cb.shape
+    accumulate = z_q is not None
+    if z_q is None:
+        z_q = torch.empty((N, C), device=idx.device, dtype=torch.float32)
+    bad = torch.zeros((1,), device=idx.device, dtype=torch.int32) if check_range else None
+    check(load_library().bc_vq_dequant(ptr(idx), ptr(cb), ptr(w_out), ptr(b_out), ptr(z_q), ptr(residual), ptr(bad),
+                                       N, C, D, Kc, int(accumulate), stream_ptr(idx.device)), "bc_vq_dequant")
+    _count()
+    if check_range and int(bad.item()) != 0:
+        raise IndexError(f"vq_dequant: {int(bad.item())} indices outside [0, {Kc})")
+    return z_q
+
+
+def indices_to_int16(idx: torch.Tensor) -> torch.Tensor:
+    """int32 [n_q, N] -> int16 [N, n_q] (extract_indices.py:520-532 layout)."""
+    require_cuda(idx, "idx")
+    idx = idx.to(torch.int32).contiguous()
+    n_q, N = idx.shape
+    out = torch.empty((N, n_q), device=idx.device, dtype=torch.int16)
+    check(load_library().bc_indices_to_int16(ptr(idx), ptr(out), n_q, N, stream_ptr(idx.device)), "bc_indices_to_int16")
+    _count()
+    return out

@@ -1,0 +1,69 @@
+"""BigCodecEncoder (host mirror of vq/codec_encoder.py:14-90).
+
+waveform [B,1,T] -> conv stem -> EncoderBlocks -> [ResLSTM] -> SnakeBeta -> conv ->
+latents [B,out_channels,T'].  Same constructor, attributes and state-dict keys as the
+reference; the arithmetic runs in the sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from . import activations
+from .alias_free_torch import Activation1d
+from .module import EncoderBlock, ResLSTM, WNConv1d, _act_conv
+
+
+class BigCodecEncoder(nn.Module):
+    def __init__(self, ngf=48, use_rnn=True, rnn_bidirectional=False, causal=False, antialias=False,
+                 rnn_num_layers=2, up_ratios=(2, 2, 2, 5, 5), dilations=(1, 3, 9), out_channels=1024):
+        super().__init__()
+        self.hop_length = np.prod(up_ratios)
+        self.ngf = ngf
+        self.up_ratios = up_ratios
+        if causal:
+            assert not rnn_bidirectional
+        d_model = ngf
+        block = [WNConv1d(1, d_model, kernel_size=7, padding=3, causal=causal)]
+        for stride in up_ratios:
+            d_model *= 2
+            block += [EncoderBlock(d_model, stride=stride, dilations=dilations, causal=causal, antialias=antialias)]
+        if use_rnn:
+            block += [ResLSTM(d_model, num_layers=rnn_num_layers, bidirectional=rnn_bidirectional)]
+        block += [
+            Activation1d(activation=activations.SnakeBeta(d_model, alpha_logscale=True), antialias=antialias),
+            WNConv1d(d_model, out_channels, kernel_size=3, padding=1, causal=causal),
+        ]
+        self.block = nn.Sequential(*block)
+        self.enc_dim = d_model
+        self.eval()
+
+    def forward_cl(self, x_cl):
+        """x_cl [B,T,1] -> latents [B,T',out_channels] (channels-last)."""
+        mods = list(self.block)
+        h = mods[0].forward_cl(x_cl)
+        for m in mods[1:-2]:
+            h = m.forward_cl(h)
+        return _act_conv(mods[-2], mods[-1], h)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x float32 [B,1,T] -> [B,out_channels,T'] (a channels-last-strided view; values as the reference)."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"BigCodecEncoder expects [B,1,T], got {tuple(x.shape)}")
+        return self.forward_cl(ops.to_channels_last(x)).permute(0, 2, 1)
+
+    def inference(self, x):
+        return self.forward(x)
+
+    # weight-norm is folded once at load time; these exist for API compatibility
+    def remove_weight_norm(self):
+        """No-op: the kernels always consume the folded weight (g*v/||v||)."""
+
+    def apply_weight_norm(self):
+        """No-op: parameters are always stored as weight_g / weight_v."""
+
+    def reset_parameters(self):
+        """The reference re-initialises a derived attribute here (SURVEY.md 8c hazard 1); nothing to do."""

@@ -1,0 +1,346 @@
+"""Conv / residual / LSTM building blocks (host mirror of vq/module.py:11-167).
+
+Same class names, constructor arguments, parameter names and shapes as the
+reference, so a reference ``state_dict`` loads unchanged (old-style weight-norm
+triples ``weight_g / weight_v / bias``).  ``forward`` takes and returns the
+reference's ``[B, C, T]`` tensors; internally everything runs channels-last
+through the C ABI (``forward_cl``), with SnakeBeta fused into the consuming conv
+and bias / residual / tanh fused into its epilogue.
+
+Inference only: parameters do not require grad and no autograd graph is built.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from .. import ops
+from . import activations
+from .alias_free_torch import Activation1d
+
+_PRECISION = ["fp32"]
+
+
+def set_precision(mode: str) -> None:
+    """Arithmetic mode of the dense contractions: 'fp32' (CUDA cores, exact float32),
+    'bf16' (tcgen05 single pass) or 'bf16x3' (tcgen05 split-precision)."""
+    if mode not in ops.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)}")
+    _PRECISION[0] = mode
+
+
+def get_precision() -> str:
+    return _PRECISION[0]
+
+
+def _fold(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """weight_norm(dim=0): w = g * v / ||v|| with the norm over all dims but 0 (float64 fold, once per load)."""
+    v64, g64 = v.detach().double(), g.detach().double()
+    norm = v64.flatten(1).norm(dim=1).view([-1] + [1] * (v64.dim() - 1))
+    return v64 * (g64 / norm)
+
+
+class _WNParams(nn.Module):
+    """weight_g / weight_v / bias holder with a packed-weight cache."""
+
+    def _key(self):
+        return (self.weight_g._version, self.weight_v._version, self.bias._version, self.weight_v.data_ptr(),
+                self.weight_v.device)
+
+    def _cached(self, build):
+        key = self._key()
+        c = getattr(self, "_pack_cache", None)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                c = (key,) + tuple(build())
+            self._pack_cache = c
+        return c[1:]
+
+    @property
+    def weight(self):
+        """Folded weight in the reference's layout (derived, like old-style weight_norm's ``.weight``)."""
+        return _fold(self.weight_g, self.weight_v).float()
+
+
+class _Conv1dWN(_WNParams):
+    """weight_norm(nn.Conv1d) (vq/module.py:59-65).  ``left_pad`` overrides symmetric padding (causal)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, left_pad=None):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.left_pad = padding if left_pad is None else left_pad
+        self.total_pad = 2 * padding if left_pad is None else left_pad
+        bound = 1.0 / math.sqrt(in_channels * kernel_size)
+        v = (torch.rand(out_channels, in_channels, kernel_size) * 2 - 1) * bound
+        self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).view(-1, 1, 1), requires_grad=False)
+        self.weight_v = nn.Parameter(v, requires_grad=False)
+        self.bias = nn.Parameter(torch.zeros(out_channels), requires_grad=False)
+
+    def out_length(self, t_in: int) -> int:
+        return (t_in + self.total_pad - self.dilation * (self.kernel_size - 1) - 1) // self.stride + 1
+
+    def packed(self):
+        def build():
+            w = _fold(self.weight_g, self.weight_v)                 # [out, in, k]
+            return (w.permute(2, 1, 0).contiguous().float(),        # [k, in, out]
+                    self.bias.detach().float().contiguous())
+        return self._cached(build)
+
+    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None, res=None, tanh=False):
+        w, b = self.packed()
+        a = ib = None
+        if act is not None:
+            a, ib = act.device_params()
+        return ops.conv1d(x_cl, w, b, stride=self.stride, dilation=self.dilation, pad_left=self.left_pad,
+                          t_out=self.out_length(x_cl.shape[1]), snake_a=a, snake_ib=ib, res=res, tanh=tanh,
+                          precision=get_precision())
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class _ConvTranspose1dWN(_WNParams):
+    """weight_norm(nn.ConvTranspose1d) (vq/module.py:67-72): weight [in, out, k], norm per INPUT channel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, causal_trim=0):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.stride, self.padding, self.output_padding, self.causal_trim = stride, padding, output_padding, causal_trim
+        bound = 1.0 / math.sqrt(out_channels * kernel_size)
+        v = (torch.rand(in_channels, out_channels, kernel_size) * 2 - 1) * bound
+        self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).view(-1, 1, 1), requires_grad=False)
+        self.weight_v = nn.Parameter(v, requires_grad=False)
+        self.bias = nn.Parameter((torch.rand(out_channels) * 2 - 1) * bound, requires_grad=False)
+        s, k = stride, kernel_size
+        t_out_minus = -s - 2 * padding + k + output_padding - causal_trim   # T_out = T_in*s + this
+        if s == 1 or k != 2 * s or t_out_minus != 0:
+            raise NotImplementedError(
+                f"ConvTranspose1d(k={k}, stride={s}, padding={padding}, output_padding={output_padding}): only the "
+                "codec's k = 2*stride up-sampling geometry (T_out = T_in*stride) is implemented")
+
+    def packed(self):
+        def build():
+            w = _fold(self.weight_g, self.weight_v)                 # [in, out, k]
+            s, p = self.stride, self.padding
+            phases = []
+            for ph in range(s):
+                j0 = (ph + p) % s
+                phases.append(torch.stack([w[:, :, j0 + s], w[:, :, j0]]))   # tap0 -> x[m+q-1], tap1 -> x[m+q]
+            return (torch.stack(phases).contiguous().float(),       # [s, 2, in, out]
+                    self.bias.detach().float().contiguous())
+        return self._cached(build)
+
+    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None):
+        w, b = self.packed()
+        a = ib = None
+        if act is not None:
+            a, ib = act.device_params()
+        return ops.conv_transpose1d(x_cl, w, b, stride=self.stride, padding=self.padding, snake_a=a, snake_ib=ib,
+                                    precision=get_precision())
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class CausalConv1d(nn.Module):
+    """Left-padded conv (vq/module.py:11-48); parameters live under ``.conv`` like the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding=0, stride=1, dilation=1, groups=1, bias=True,
+                 padding_mode="zeros", device=None, dtype=None):
+        super().__init__()
+        if groups != 1 or not bias or padding_mode != "zeros":
+            raise NotImplementedError("CausalConv1d: only groups=1, bias=True, zero padding are on the hot path")
+        self.padding = (kernel_size - stride) * dilation
+        self.conv = _Conv1dWN(in_channels, out_channels, kernel_size, stride=stride, padding=0, dilation=dilation,
+                              left_pad=self.padding)
+
+    def forward_cl(self, x_cl, act=None, res=None, tanh=False):
+        return self.conv.forward_cl(x_cl, act=act, res=res, tanh=tanh)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class CausalConvTranspose1d(nn.Module):
+    """ConvTranspose1d without padding, last ``stride`` samples dropped (vq/module.py:50-57)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, bias=True, device=None, dtype=None):
+        super().__init__()
+        if not bias:
+            raise NotImplementedError("CausalConvTranspose1d: bias=False is not on the hot path")
+        self.stride = stride
+        self.conv = _ConvTranspose1dWN(in_channels, out_channels, kernel_size, stride=stride, padding=0,
+                                       output_padding=0, causal_trim=stride)
+
+    def forward_cl(self, x_cl, act=None):
+        return self.conv.forward_cl(x_cl, act=act)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+def WNConv1d(*args, causal=False, **kwargs):
+    """Factory with the reference's signature (vq/module.py:59-65)."""
+    if causal:
+        return CausalConv1d(*args, **kwargs)
+    return _Conv1dWN(*args, **kwargs)
+
+
+def WNConvTranspose1d(*args, causal=False, **kwargs):
+    """Factory with the reference's signature (vq/module.py:67-72)."""
+    if causal:
+        return CausalConvTranspose1d(*args, **kwargs)
+    return _ConvTranspose1dWN(*args, **kwargs)
+
+
+def _act_conv(act: Activation1d, conv, x_cl, **kw):
+    """Activation1d followed by a conv: fused prologue when not anti-aliased."""
+    if act.antialias:
+        return conv.forward_cl(act.forward_cl(x_cl), **kw)
+    return conv.forward_cl(x_cl, act=act.act, **kw)
+
+
+class ResidualUnit(nn.Module):
+    """x + conv1(snake(conv7_dilated(snake(x))))  (vq/module.py:74-89)."""
+
+    def __init__(self, dim: int = 16, dilation: int = 1, causal: bool = False, antialias: bool = False):
+        super().__init__()
+        pad = 0 if causal else ((7 - 1) * dilation) // 2
+        self.block = nn.Sequential(
+            Activation1d(activation=activations.SnakeBeta(dim, alpha_logscale=True), antialias=antialias),
+            WNConv1d(dim, dim, kernel_size=7, dilation=dilation, padding=pad, causal=causal),
+            Activation1d(activation=activations.SnakeBeta(dim, alpha_logscale=True), antialias=antialias),
+            WNConv1d(dim, dim, kernel_size=1),
+        )
+
+    def forward_cl(self, x_cl):
+        h = _act_conv(self.block[0], self.block[1], x_cl)
+        return _act_conv(self.block[2], self.block[3], h, res=x_cl)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class EncoderBlock(nn.Module):
+    """3 ResidualUnits -> snake -> strided conv (vq/module.py:91-113)."""
+
+    def __init__(self, dim: int = 16, stride: int = 1, dilations=(1, 3, 9), causal: bool = False,
+                 antialias: bool = False):
+        super().__init__()
+        runits = [ResidualUnit(dim // 2, dilation=d, causal=causal, antialias=antialias) for d in dilations]
+        pad = 0 if causal else (stride // 2 + stride % 2 if stride != 1 else 0)
+        self.block = nn.Sequential(
+            *runits,
+            Activation1d(activation=activations.SnakeBeta(dim // 2, alpha_logscale=True), antialias=antialias),
+            WNConv1d(dim // 2, dim, kernel_size=2 * stride if stride != 1 else 1, stride=stride, padding=pad,
+                     causal=causal),
+        )
+
+    def forward_cl(self, x_cl):
+        n = len(self.block)
+        for ru in list(self.block)[: n - 2]:
+            x_cl = ru.forward_cl(x_cl)
+        return _act_conv(self.block[n - 2], self.block[n - 1], x_cl)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class DecoderBlock(nn.Module):
+    """snake -> transposed conv -> 3 ResidualUnits (vq/module.py:115-141)."""
+
+    def __init__(self, input_dim: int = 16, output_dim: int = 8, stride: int = 1, dilations=(1, 3, 9),
+                 causal: bool = False, antialias: bool = False):
+        super().__init__()
+        if causal:
+            tconv_kwargs = {}
+        else:
+            tconv_kwargs = {"padding": stride // 2 + stride % 2 if stride != 1 else 0,
+                            "output_padding": stride % 2 if stride != 1 else 0}
+        self.block = nn.Sequential(
+            Activation1d(activation=activations.SnakeBeta(input_dim, alpha_logscale=True), antialias=antialias),
+            WNConvTranspose1d(input_dim, output_dim, kernel_size=2 * stride if stride != 1 else 1, stride=stride,
+                              causal=causal, **tconv_kwargs),
+        )
+        self.block.extend([ResidualUnit(output_dim, dilation=d, causal=causal, antialias=antialias)
+                           for d in dilations])
+
+    def forward_cl(self, x_cl):
+        act, up = self.block[0], self.block[1]
+        if act.antialias:
+            h = up.forward_cl(act.forward_cl(x_cl))
+        else:
+            h = up.forward_cl(x_cl, act=act.act)
+        for ru in list(self.block)[2:]:
+            h = ru.forward_cl(h)
+        return h
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))
+
+
+class _LSTMParams(nn.Module):
+    """Parameter holder with nn.LSTM's names (weight_ih_l{k}, weight_hh_l{k}, bias_ih_l{k}, bias_hh_l{k})."""
+
+    def __init__(self, input_size, hidden_size, num_layers):
+        super().__init__()
+        self.input_size, self.hidden_size, self.num_layers = input_size, hidden_size, num_layers
+        bound = 1.0 / math.sqrt(hidden_size)
+        for l in range(num_layers):
+            in_f = input_size if l == 0 else hidden_size
+            for name, shape in (("weight_ih", (4 * hidden_size, in_f)), ("weight_hh", (4 * hidden_size, hidden_size)),
+                                ("bias_ih", (4 * hidden_size,)), ("bias_hh", (4 * hidden_size,))):
+                self.register_parameter(f"{name}_l{l}", nn.Parameter((torch.rand(shape) * 2 - 1) * bound,
+                                                                     requires_grad=False))
+
+    def packed(self, layer: int):
+        ps = [getattr(self, f"{n}_l{layer}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        key = tuple(p._version for p in ps) + (ps[0].data_ptr(), ps[0].device)
+        cache = self.__dict__.setdefault("_pack_cache", {})
+        c = cache.get(layer)
+        if c is None or c[0] != key:
+            with torch.no_grad():
+                w_ih, w_hh, b_ih, b_hh = [p.detach().float() for p in ps]
+                H = self.hidden_size
+                w_in = w_ih.t().contiguous().unsqueeze(0)                       # [1, in, 4H] (K = 1 conv)
+                bias = (b_ih + b_hh).contiguous()
+                # packed[cta][j][u*4+g] = w_hh[g*H + cta*4 + u][j]   (bc_lstm_pack_whh layout)
+                w_rec = w_hh.view(4, H // 4, 4, H).permute(1, 3, 2, 0).contiguous()
+            c = (key, w_in, bias, w_rec)
+            cache[layer] = c
+        return c[1:]
+
+
+class ResLSTM(nn.Module):
+    """y = LSTM(x^T) + x^T (vq/module.py:143-167); uni-directional only on the hot path."""
+
+    def __init__(self, dimension: int, num_layers: int = 2, bidirectional: bool = False, skip: bool = True):
+        super().__init__()
+        if bidirectional:
+            raise NotImplementedError("bidirectional ResLSTM is not used by any codec config and is not implemented")
+        self.skip = skip
+        self.lstm = _LSTMParams(dimension, dimension, num_layers)
+
+    def forward_cl(self, x_cl):
+        h = x_cl
+        n = self.lstm.num_layers
+        for l in range(n):
+            w_in, bias, w_rec = self.lstm.packed(l)
+            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=get_precision())
+            h = ops.lstm_recurrent(pre, w_rec, x_cl if (self.skip and l == n - 1) else None)
+        return h
+
+    @torch.no_grad()
+    def forward(self, x):  # [B, F, T]
+        return ops.to_channels_first(self.forward_cl(ops.to_channels_last(x)))

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- encode -> VQ-indices throughput of the BigCodec hot path on N B200s.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (N > 1 under torchrun, one rank per
+GPU) prints ONE JSON line on rank 0.  A "step" is one pass of waveform -> encoder -> VQ indices
+over this rank's shard of BASELINE.json configs[1]: 4096 synthetic 30 s 16 kHz clips sharded by
+utterance over 8 GPUs = 512 clips (15 360 audio-seconds) per GPU, weak scaling.
+
+  value     whole-job audio-seconds per wall-second, inputs resident in HBM, CUDA events, max over ranks
+  e2e       the same through the host-buffer API (BigCodecModel.extract_indices): pinned host waveforms
+            -> H2D -> encode -> int16 indices -> D2H, copies inside the timed region
+  roofline  the dense-contraction kernels (conv / transposed conv / LSTM input projection) vs the
+            measured bf16 tensor peak: algorithmic FLOPs / CUDA-event time of those launches
+  cpu_baseline   the CPU oracle port (torch CPU library calls, the reference's own arithmetic) on the
+            host cores, bounded sample (rank 0, N = 1)
+
+``--impl reference`` times the CPU implementation only (the reference's PyTorch-CPU arithmetic as
+restated in oracle/; /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+METRIC = "audio_seconds_encoded_to_indices_per_second"
+UNIT = "audio-s/s"
+ENC_GFLOP_PER_AUDIO_S = {"base": 6.860 + 0.012, "debug": 3.523 + 0.007, "config9_base": 4.175 + 0.007,
+                         "default": 50.983 + 0.013}   # BASELINE.md section 3 (encoder + VQ)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="base")
+    ap.add_argument("--precision", default=os.environ.get("BC_PRECISION", "fp32"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--clips-per-gpu", type=int, default=512)
+    ap.add_argument("--clip-seconds", type=float, default=30.0)
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("BC_MICRO_BATCH", "8")))
+    ap.add_argument("--cpu-sample-clips", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        # "under load": drop samples far below the maximum seen while busy
+        busy = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_encode_rate(cfg, enc_sd, dec_sd, clips, clip_samples, reps=1):
+    """audio-s/s of the CPU oracle port on this host: ``clips`` x ``clip_samples`` per pass."""
+    from audiotokenization_b200 import synth
+    from oracle import bigcodec_oracle as oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = synth.fast_synth_batch(0, clips, clip_samples)
+    with torch.no_grad():
+        oracle.encode_to_indices(enc_sd, dec_sd, cfg, x[:1, :, : min(clip_samples, 32000)])  # warm-up (thread pools)
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = oracle.encode_to_indices(enc_sd, dec_sd, cfg, x)
+            best = min(best, time.perf_counter() - t0)
+    assert out["indices"].shape[-1] > 0
+    return clips * clip_samples / 16000.0 / best, best
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """CPU arm: the reference's PyTorch-CPU arithmetic (oracle port), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from audiotokenization_b200 import configs, synth
+    cfg = configs.get_config(args.model)
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=0)
+    clip_samples = int(round(args.clip_seconds * 16000))
+    clips = args.cpu_sample_clips
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        cpu_encode_rate(cfg, enc_sd, dec_sd, 1, clip_samples)
+    times = []
+    for _ in range(args.steps):
+        _, t = cpu_encode_rate(cfg, enc_sd, dec_sd, clips, clip_samples)
+        times.append(t)
+    total = sum(times)
+    value = args.steps * clips * args.clip_seconds / total
+    sample = f"{clips} of the {args.clips_per_gpu} clips x {args.clip_seconds:g} s per step (bounded sample of the same workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world, "fp32"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world, precision):
+    return {"workload": "configs[1]: batched encode->indices of 4096 synthetic 30 s 16 kHz clips sharded by utterance "
+                        "across 8xB200 (512 clips per GPU, weak scaling)",
+            "model": f"BigCodec {args.model} (cfgs/config11/model/base.yaml)" if args.model == "base" else args.model,
+            "clips_per_gpu": args.clips_per_gpu, "clip_seconds": args.clip_seconds, "sample_rate": 16000,
+            "global_clips": args.clips_per_gpu * world, "micro_batch": args.micro_batch, "precision": precision,
+            "weights": "random-init, seed 0 (biases / snake alpha,beta / weight-norm gains randomised)",
+            "l2_policy": "inputs_larger_than_l2 (983 MB of waveforms per step; every activation tensor > 126 MB)",
+            "parallelism": f"utterance-sharded x{world}, no collective on the data path"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from audiotokenization_b200 import configs, ops, synth
+    from audiotokenization_b200.model import BigCodecModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    cfg = configs.get_config(args.model)
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=0)
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device=str(dev), precision=args.precision)
+    clip_samples = int(round(args.clip_seconds * 16000))
+    n_local = args.clips_per_gpu
+    first = rank * n_local                       # this rank's shard of the global utterance list
+    host = torch.empty((n_local, 1, clip_samples), dtype=torch.float32, pin_memory=True)
+    synth.fast_synth_batch(first, n_local, clip_samples, out=host)
+    x_dev = host.to(dev)
+    audio_s_local = n_local * args.clip_seconds
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    keep = {}
+
+    def step_device():
+        keep["idx"] = model.indices_device(x_dev, micro_batch=args.micro_batch)
+
+    for _ in range(args.warmup):
+        step_device()
+    ops.STATS["launches"] = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.STATS["launches"]
+    value = world * audio_s_local * args.steps / (ms_total / 1000.0)
+
+    # ---- end to end through the host-buffer API ----------------------------------------------
+    def step_e2e():
+        keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * audio_s_local * args.steps / (ms_e2e / 1000.0)
+    i16 = keep["i16"]
+    same = bool((keep["idx"].cpu().numpy() == i16).all())
+
+    # ---- roofline of the dense-contraction kernels (one instrumented step) ---------------------
+    ops.PROFILE = []
+    step_device()
+    torch.cuda.synchronize(dev)
+    prof, ops.PROFILE = ops.PROFILE, None
+    by_kind = {}
+    for kind, flops, a, b in prof:
+        d = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += flops
+        d[1] += a.elapsed_time(b)
+        d[2] += 1
+    conv_flops = sum(v[0] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
+    conv_ms = sum(v[1] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
+    step_ms = ms_total / args.steps
+    peaks = load_peaks()
+    achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv1d (dense contractions incl. LSTM input projection)",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                "launches_per_step": sum(v[2] for k, v in by_kind.items() if k in ("conv1d", "convtr1d")),
+                "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms if step_ms else None,
+                "lstm_ms_per_step": by_kind.get("lstm", [0, 0, 0])[1],
+                "whole_step_frac": (value / world) * ENC_GFLOP_PER_AUDIO_S.get(args.model, 0.0) / 1e3
+                / peaks["bf16_tflops_sustained"]}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        clips = args.cpu_sample_clips
+        v, t = cpu_encode_rate(cfg, enc_sd, dec_sd, clips, clip_samples, reps=2)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"{clips} of the {n_local} clips x {args.clip_seconds:g} s, best of 2 passes "
+                                  f"({t:.1f} s per pass), oracle/bigcodec_oracle.py (torch CPU fp32)",
+                        }
+        # parity spot-check of the benchmarked run against the oracle on the sample
+        from oracle import bigcodec_oracle as oracle
+        with torch.no_grad():
+            want = oracle.encode_to_indices(enc_sd, dec_sd, cfg, host[:1])
+        got = torch.from_numpy(i16[:1, :, 0].astype("int64"))
+        decided = want["margin"][0] > 1e-5
+        cpu_baseline["parity_clip0"] = {
+            "index_agreement": float((got == want["indices"][0]).float().mean()),
+            "exact_where_margin_gt_1e-5": bool(torch.equal(got[decided], want["indices"][0][decided]))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3(f32-class)"}[args.precision], "data": "synthetic",
+            "config": workload_config(args, world, args.precision),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
+                    "d2h_bytes_per_step": int(i16.nbytes), "ms_per_step": ms_e2e / args.steps,
+                    "matches_device_path": same},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

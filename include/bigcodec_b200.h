@@ -1,0 +1,157 @@
+/*
+ * bigcodec_b200.h -- C ABI of the B200-native BigCodec audio-tokenizer hot path.
+ *
+ * The reference (hoyso48/AudioTokenization, BigCodec_SSL/) has no FFI layer: its
+ * boundary is the Python nn.Module API of the `vq/` package, and every numeric
+ * step below is a PyTorch library call there.  Each entry point names the
+ * reference call site(s) it replaces (paths relative to BigCodec_SSL/).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, ints, an opaque stream handle (cudaStream_t).
+ *     No torch / C++ types cross this boundary.
+ *   - activations are float32, CHANNELS-LAST: x[b][t][c]  (the reference uses
+ *     [b][c][t]; bc_transpose_* converts at the module boundary).
+ *   - weights are pre-folded (weight_norm g*v/||v|| is done once on the host,
+ *     SURVEY.md App. C) and packed tap-major: w[k][c_in][c_out].
+ *   - every function returns 0 on success, a negative BC_E* code on bad
+ *     arguments / unsupported configuration, or a positive cudaError_t value.
+ *     Nothing aborts; bc_last_error() returns a thread-local message.
+ *   - re-entrant, asynchronous on `stream`, no hidden synchronisation, no
+ *     allocation (callers pass workspaces), no global mutable state.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns an error.
+ */
+#ifndef BIGCODEC_B200_H
+#define BIGCODEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_ABI_VERSION 3
+
+typedef void* bc_stream_t; /* cudaStream_t */
+
+enum {
+  BC_OK = 0,
+  BC_EINVAL = -1,       /* bad shape / null pointer / misaligned pointer */
+  BC_EUNSUPPORTED = -2, /* valid in the reference, not implemented here (e.g. bidirectional LSTM) */
+  BC_ENODEVICE = -3     /* no CUDA device / wrong architecture */
+};
+
+/* flags for bc_conv1d_fwd */
+enum {
+  BC_CONV_SNAKE_IN = 1, /* apply SnakeBeta to the input while staging it (needs snake_a, snake_ib) */
+  BC_CONV_TANH_OUT = 2, /* y = tanh(y) after bias/residual (decoder tail, vq/codec_decoder.py:78) */
+  BC_CONV_ACCUM_OUT = 4 /* y += result (internal use) */
+};
+
+/* arithmetic mode of the dense contractions */
+enum {
+  BC_PREC_FP32 = 0,   /* CUDA-core FFMA, exact float32 (parity mode) */
+  BC_PREC_BF16 = 1,   /* tcgen05 bf16 x bf16 -> fp32, single pass (fast mode) */
+  BC_PREC_BF16X3 = 2  /* tcgen05, hi/lo split: hi*hi + hi*lo + lo*hi (fp32-class accuracy on tensor cores) */
+};
+
+int bc_abi_version(void);
+const char* bc_last_error(void);
+/* 0 if device `dev` exists and is sm_100; fills optional outputs. */
+int bc_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- layout ------------------------------------------------------------- */
+/* [B,C,T] -> [B,T,C] and back (module boundary: the reference's tensors are [B,C,T],
+ * vq/codec_encoder.py:62-64, vq/codec_decoder.py:85-94). */
+int bc_transpose_bct_to_btc(const float* x, float* y, int B, int C, int T, bc_stream_t s);
+int bc_transpose_btc_to_bct(const float* x, float* y, int B, int T, int C, bc_stream_t s);
+
+/* ---- SnakeBeta / anti-aliased Activation1d ------------------------------ */
+/* Replaces Activation1d.forward (vq/alias_free_torch/act.py:25-32) wrapping
+ * SnakeBeta(alpha_logscale=True).forward (vq/activations.py:107-119):
+ *   y = x + snake_ib[c] * sin(x * snake_a[c])^2,  snake_a = exp(alpha), snake_ib = 1/(exp(beta)+1e-9).
+ * antialias != 0 additionally applies UpSample1d (resample.py:25-33) before and
+ * DownSample1d/LowPassFilter1d (resample.py:47-49, filter.py:86-95) after, fused in
+ * one pass; fir12 = the 12 Kaiser-sinc taps (filter.py:28-57), a DEVICE pointer.
+ * x, y: [B,T,C] channels-last; y may not alias x when antialias != 0. */
+int bc_snake_fwd(const float* x, float* y, const float* snake_a, const float* snake_ib,
+                 const float* fir12, int B, int T, int C, int antialias, bc_stream_t s);
+
+/* ---- dense convolutions -------------------------------------------------- */
+/* Replaces nn.Conv1d under WNConv1d / CausalConv1d (vq/module.py:11-48,59-65) and, with
+ * the phase decomposition of bc_convtr1d_fwd, nn.ConvTranspose1d (vq/module.py:50-57,67-72).
+ *
+ *   y[b][t*y_tstride + y_toffset][co] = bias[co]
+ *        + sum_{k<K} sum_{ci<C_in} w[k][ci][co] * act(x[b][t*stride + k*dilation - pad_left][ci])
+ *        (+ res[b][same row][co])                       for t in [0, T_out)
+ * rows outside [0, T_in) read as zero AFTER the activation (the reference zero-pads the
+ * activation's output).  act = SnakeBeta if BC_CONV_SNAKE_IN else identity.
+ * y has y_rows rows per batch item (y_rows >= (T_out-1)*y_tstride + y_toffset + 1).
+ * res (optional) has the same geometry as y.  bias may be NULL. */
+int bc_conv1d_fwd(const float* x, const float* w, const float* bias,
+                  const float* snake_a, const float* snake_ib, const float* res, float* y,
+                  int B, int T_in, int C_in, int T_out, int C_out, int K, int stride, int dilation,
+                  int pad_left, int y_rows, int y_tstride, int y_toffset, int flags, int precision,
+                  bc_stream_t s);
+
+/* Transposed conv as `stride` output phases of 2-tap convs:
+ * w_phases[phase][2][C_in][C_out] (host-packed from the folded [C_in,C_out,2*stride]
+ * weight: tap0 = W[:,:,j0+stride], tap1 = W[:,:,j0], j0 = (phase+padding) % stride).
+ * T_out = T_in*stride for both the padded (padding = ceil(stride/2), output_padding =
+ * stride%2; vq/module.py:119-136) and the causal (padding 0, last `stride` samples
+ * dropped; vq/module.py:50-57) variants. */
+int bc_convtr1d_fwd(const float* x, const float* w_phases, const float* bias,
+                    const float* snake_a, const float* snake_ib, float* y,
+                    int B, int T_in, int C_in, int C_out, int stride, int padding, int flags,
+                    int precision, bc_stream_t s);
+
+/* ---- LSTM ---------------------------------------------------------------- */
+/* One uni-directional LSTM layer, recurrent part (nn.LSTM inside ResLSTM,
+ * vq/module.py:143-167; gate order i,f,g,o; h0 = c0 = 0).
+ *   pre   [B][T][4H]  = W_ih x_t + b_ih + b_hh for all t (computed by bc_conv1d_fwd, K=1)
+ *   w_hh_packed       = bc_lstm_pack_whh layout of W_hh [4H][H]
+ *   skip  [B][T][H]   optional, added to the output (ResLSTM's `y + x`, last layer only)
+ *   y     [B][T][H]
+ *   workspace: bc_lstm_workspace_bytes(B,H) bytes, device, need not be zeroed.
+ * Launched as ONE cooperative persistent kernel (grid-wide sync per time step). */
+size_t bc_lstm_workspace_bytes(int B, int H);
+size_t bc_lstm_packed_whh_floats(int H);
+/* host-side helper: w_hh [4H][H] row-major (host ptr) -> packed (host ptr) */
+int bc_lstm_pack_whh(const float* w_hh, float* packed, int H);
+int bc_lstm_recurrent_fwd(const float* pre, const float* w_hh_packed, const float* skip, float* y,
+                          void* workspace, int B, int T, int H, bc_stream_t s);
+
+/* ---- factorized VQ -------------------------------------------------------- */
+/* Replaces FactorizedVectorQuantize.forward / decode_latents in eval mode
+ * (vq/factorized_vector_quantize.py:29-76,93-109): in_proj -> L2 normalise -> nearest
+ * code by cosine (== argmax(-dist), ties -> lowest index) -> int32 index.
+ *   z        [N][C] channels-last latents (N = B*T')
+ *   w_in     [D][C] folded in_proj weight, b_in [D]   (NULL,NULL => identity, C == D)
+ *   cb_norm  [Kc][D] codebook rows L2-normalised with F.normalize's eps (1e-12)
+ *   idx      [N] int32 out
+ *   margin   [N] optional: top-1 minus top-2 cosine
+ *   z_e      [N][D] optional: projected (un-normalised) latents
+ * D must be <= 16; Kc >= 2. */
+int bc_vq_encode(const float* z, const float* w_in, const float* b_in, const float* cb_norm,
+                 int32_t* idx, float* margin, float* z_e, int N, int C, int D, int Kc,
+                 bc_stream_t s);
+
+/* Replaces embed_code + out_proj (factorized_vector_quantize.py:72-74,78-91) and one
+ * iteration of the ResidualVQ loop (vq/residual_vq.py:27-33):
+ *   q[n][c] = b_out[c] + sum_d w_out[c][d] * cb[idx[n]][d]      (cb = RAW codebook rows)
+ *   z_q[n][c]       = (accumulate ? z_q[n][c] : 0) + q[n][c]
+ *   residual[n][c] -= q[n][c]                                   (if residual != NULL)
+ * w_out NULL => identity (C == D).  Out-of-range indices return BC_EINVAL lazily:
+ * they are clamped on the device and counted into *bad_count (optional, device int). */
+int bc_vq_dequant(const int32_t* idx, const float* cb, const float* w_out, const float* b_out,
+                  float* z_q, float* residual, int* bad_count, int N, int C, int D, int Kc,
+                  int accumulate, bc_stream_t s);
+
+/* int32 [n_q][N] indices -> int16 [N][n_q], the on-disk layout of extract_indices.py:520-532. */
+int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIGCODEC_B200_H */

@@ -1,0 +1,256 @@
+"""GPU: per-operator parity of the CUDA kernels (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Float32 mode: tolerances are float32 rounding (<= 2e-5 relative, far
+inside the 1e-3 the north star states); integer outputs are bit-exact (margin-gated for argmax)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from audiotokenization_b200 import configs, ops, synth
+from audiotokenization_b200.vq import module as M
+from audiotokenization_b200.vq import (Activation1d, BigCodecDecoder, FactorizedVectorQuantize, ResidualVQ, SnakeBeta)
+from oracle import bigcodec_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-5
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def gen(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+def test_device_is_sm100():
+    from audiotokenization_b200 import _cabi
+    info = _cabi.device_info(0)
+    assert info["cc"][0] == 10 and info["sm_count"] >= 100
+
+
+@pytest.mark.parametrize("B,C,T", [(1, 1, 17), (2, 32, 1000), (3, 33, 129), (1, 512, 80), (2, 7, 31)])
+def test_transpose_round_trip(B, C, T):
+    x = torch.randn(B, C, T, generator=gen(1)).to(DEV)
+    cl = ops.to_channels_last(x)
+    assert cl.shape == (B, T, C) and torch.equal(cl, x.permute(0, 2, 1))
+    back = ops.to_channels_first(cl.contiguous())
+    assert torch.equal(back, x)
+
+
+@pytest.mark.parametrize("aa", [False, True])
+@pytest.mark.parametrize("B,C,T", [(1, 8, 1), (2, 32, 5), (1, 33, 31), (2, 64, 33), (1, 32, 1000), (3, 128, 257),
+                                   (1, 4, 4099)])
+def test_activation1d_matches_oracle(aa, B, C, T):
+    g = gen(B * 1000 + C + T)
+    act = Activation1d(SnakeBeta(C, alpha_logscale=True), antialias=aa)
+    act.act.alpha.data = torch.randn(C, generator=g) * 0.3
+    act.act.beta.data = torch.randn(C, generator=g) * 0.3
+    x = torch.randn(B, C, T, generator=g) * 1.5
+    sd = {"act.alpha": act.act.alpha.data.clone(), "act.beta": act.act.beta.data.clone()}
+    want = oracle.activation1d(sd, "", x, aa)
+    got = act.to(DEV)(x.to(DEV))
+    assert got.shape == want.shape
+    assert rel(got, want) <= TOL
+    assert float((got.cpu() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, dil, pad, causal, T
+    (1, 32, 7, 1, 1, 3, False, 1000),
+    (32, 32, 7, 1, 1, 3, False, 777),
+    (32, 32, 7, 1, 3, 9, False, 300),
+    (32, 32, 7, 1, 9, 27, False, 129),
+    (32, 32, 7, 1, 9, 27, False, 20),       # shorter than the receptive field
+    (64, 64, 1, 1, 1, 0, False, 513),
+    (32, 64, 4, 2, 1, 1, False, 1001),
+    (64, 128, 8, 4, 1, 2, False, 1000),
+    (128, 256, 10, 5, 1, 3, False, 999),
+    (256, 512, 10, 5, 1, 3, False, 400),
+    (512, 512, 3, 1, 1, 1, False, 80),
+    (512, 512, 7, 1, 1, 3, False, 50),
+    (32, 1, 7, 1, 1, 3, False, 1500),
+    (3, 5, 7, 1, 3, 9, False, 200),         # odd channel counts: scalar paths
+    (16, 16, 7, 1, 3, 0, True, 333),        # causal dilated
+    (16, 32, 4, 2, 1, 0, True, 335),        # causal strided
+    (8, 8, 10, 5, 1, 0, True, 64),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,pad,causal,T", CONV_CASES)
+@pytest.mark.parametrize("fused_act", [False, True])
+def test_conv1d_matches_oracle(cin, cout, k, stride, dil, pad, causal, T, fused_act):
+    g = gen(cin * 7 + cout + k + T)
+    conv = M.WNConv1d(cin, cout, kernel_size=k, stride=stride, dilation=dil, padding=pad, causal=causal)
+    inner = conv.conv if causal else conv
+    inner.weight_g.data *= torch.exp(torch.randn(cout, 1, 1, generator=g) * 0.2)
+    inner.bias.data = torch.randn(cout, generator=g) * 0.2
+    x = torch.randn(2, cin, T, generator=g)
+    sd = {("conv." if causal else "") + n: getattr(inner, n).data.clone() for n in ("weight_g", "weight_v", "bias")}
+    xin = x
+    act = None
+    if fused_act:
+        act = SnakeBeta(cin, alpha_logscale=True)
+        act.alpha.data = torch.randn(cin, generator=g) * 0.3
+        act.beta.data = torch.randn(cin, generator=g) * 0.3
+        xin = oracle.snake_beta(x, act.alpha.data, act.beta.data)
+        act = act.to(DEV)
+    want = oracle.wn_conv1d(sd, "", xin, stride=stride, dilation=dil, padding=pad, causal=causal)
+    conv = conv.to(DEV)
+    got_cl = conv.forward_cl(ops.to_channels_last(x.to(DEV)), act=act)
+    got = got_cl.permute(0, 2, 1)
+    assert got.shape == want.shape
+    assert rel(got, want) <= TOL
+
+
+def test_conv1d_residual_and_tanh_epilogues():
+    g = gen(5)
+    conv = M.WNConv1d(32, 32, kernel_size=1)
+    conv.bias.data = torch.randn(32, generator=g) * 0.1
+    x = torch.randn(2, 32, 300, generator=g)
+    r = torch.randn(2, 32, 300, generator=g)
+    sd = {n: getattr(conv, n).data.clone() for n in ("weight_g", "weight_v", "bias")}
+    want = oracle.wn_conv1d(sd, "", x) + r
+    conv = conv.to(DEV)
+    got = conv.forward_cl(ops.to_channels_last(x.to(DEV)), res=ops.to_channels_last(r.to(DEV))).permute(0, 2, 1)
+    assert rel(got, want) <= TOL
+    got_t = conv.forward_cl(ops.to_channels_last(x.to(DEV)), tanh=True).permute(0, 2, 1)
+    assert rel(got_t, torch.tanh(oracle.wn_conv1d(sd, "", x))) <= TOL
+
+
+@pytest.mark.parametrize("cin,cout,stride,causal,T", [(64, 32, 2, False, 501), (128, 64, 4, False, 250),
+                                                      (512, 256, 5, False, 80), (256, 128, 5, False, 33),
+                                                      (16, 8, 2, True, 100), (12, 6, 3, False, 50), (8, 4, 5, True, 7)])
+def test_conv_transpose1d_matches_oracle(cin, cout, stride, causal, T):
+    g = gen(cin + cout + stride + T)
+    if causal:
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, causal=True)
+        inner, pre = m.conv, "conv."
+    else:
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, padding=stride // 2 + stride % 2,
+                                output_padding=stride % 2)
+        inner, pre = m, ""
+    inner.weight_g.data *= torch.exp(torch.randn(cin, 1, 1, generator=g) * 0.2)
+    x = torch.randn(2, cin, T, generator=g)
+    act = SnakeBeta(cin, alpha_logscale=True)
+    act.alpha.data = torch.randn(cin, generator=g) * 0.3
+    act.beta.data = torch.randn(cin, generator=g) * 0.3
+    sd = {pre + n: getattr(inner, n).data.clone() for n in ("weight_g", "weight_v", "bias")}
+    want = oracle.wn_conv_transpose1d(sd, "", oracle.snake_beta(x, act.alpha.data, act.beta.data), stride=stride,
+                                      causal=causal)
+    got = m.to(DEV).forward_cl(ops.to_channels_last(x.to(DEV)), act=act.to(DEV)).permute(0, 2, 1)
+    assert got.shape == want.shape == (2, cout, T * stride)
+    assert rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("H,layers,B,T", [(64, 2, 1, 1), (64, 2, 3, 17), (64, 1, 33, 40), (512, 2, 2, 60),
+                                          (128, 2, 70, 9)])
+def test_res_lstm_matches_oracle(H, layers, B, T):
+    g = gen(H + layers + B + T)
+    m = M.ResLSTM(H, num_layers=layers)
+    sd = {"lstm." + k: v.data.clone() for k, v in m.lstm.named_parameters()}
+    x = torch.randn(B, H, T, generator=g)
+    want = oracle.res_lstm(sd, "", x, layers)
+    got = m.to(DEV)(x.to(DEV))
+    assert got.shape == want.shape
+    assert rel(got, want) <= 5e-5
+
+
+def _vq_layer(C, D, K, seed):
+    g = gen(seed)
+    layer = FactorizedVectorQuantize(dim=C, codebook_size=K, codebook_dim=D, commitment=0.25).eval()
+    layer._codebook.weight.data = torch.randn(K, D, generator=g)
+    sd = {"_codebook.weight": layer._codebook.weight.data.clone()}
+    if C != D:
+        layer.in_proj.weight_g.data *= 1.3
+        for p in ("in_proj", "out_proj"):
+            for n in ("weight_g", "weight_v", "bias"):
+                sd[f"{p}.{n}"] = getattr(getattr(layer, p), n).data.clone()
+    return layer, sd
+
+
+@pytest.mark.parametrize("C,D,K,N", [(512, 8, 8192, 800), (64, 8, 512, 203), (512, 8, 32768, 130), (8, 8, 1024, 77),
+                                     (1024, 8, 16384, 64), (32, 4, 100, 50), (48, 16, 333, 41)])
+def test_vq_encode_indices_bit_exact_where_margin_allows(C, D, K, N):
+    layer, sd = _vq_layer(C, D, K, C + K + N)
+    z = torch.randn(1, C, N, generator=gen(N))
+    z_q_want, idx_want, _, margin = oracle.vq_layer_forward(sd, "", z)
+    layer = layer.to(DEV)
+    idx, m_got, z_e = layer.encode_cl(ops.to_channels_last(z.to(DEV)), want_margin=True, want_ze=True)
+    idx, m_got = idx.cpu().long(), m_got.cpu()
+    decided = margin > 1e-5
+    assert bool(decided.float().mean() > 0.95)
+    assert torch.equal(idx[decided], idx_want[decided]), "index mismatch on a frame with margin > 1e-5"
+    assert float((idx == idx_want).float().mean()) >= 0.999
+    assert float((m_got - margin).abs().max()) <= 5e-6
+    # full forward: quantised output and the reference's return triple
+    z_q, idx2, loss = layer(z.to(DEV))
+    assert z_q.shape == z.shape and idx2.dtype == torch.int64 and float(loss.abs().sum()) == 0.0
+    same = (idx2.cpu() == idx_want).all(dim=0)
+    assert rel(z_q.cpu()[:, :, same], z_q_want[:, :, same]) <= TOL
+
+
+def test_vq_tie_break_is_lowest_index():
+    layer, sd = _vq_layer(8, 8, 64, 3)
+    cb = layer._codebook.weight.data
+    cb[40] = cb[7]          # duplicate code: both attain the maximum
+    z = cb[7].view(1, 8, 1).repeat(1, 1, 5) * 2.0
+    layer = layer.to(DEV)
+    idx, margin, _ = layer.encode_cl(ops.to_channels_last(z.to(DEV)), want_margin=True)
+    assert idx.cpu().tolist() == [[7] * 5]
+    assert float(margin.abs().max()) == 0.0
+
+
+def test_vq_dequant_and_index_entry_points():
+    cfg = configs.get_config("tiny")
+    _, dsd = synth.make_state_dicts(cfg)
+    dec = BigCodecDecoder(**cfg["codec_decoder"])
+    dec.load_state_dict(dsd)
+    dec = dec.to(DEV)
+    codes = torch.randint(0, 512, (2, 37, 1), generator=gen(2))
+    want = oracle.vq2emb(dsd, cfg["codec_decoder"], codes)
+    got = dec.vq2emb(codes.to(DEV))
+    assert got.shape == (2, 37, 64) and rel(got, want) <= TOL
+    assert torch.equal(dec.get_emb()[0].cpu(), dsd["quantizer.layers.0._codebook.weight"])
+    emb = dec.quantizer.layers[0].embed_code(codes[:, :, 0].to(DEV))
+    assert torch.equal(emb.cpu(), F.embedding(codes[:, :, 0], dsd["quantizer.layers.0._codebook.weight"]))
+    with pytest.raises(IndexError):
+        dec.vq2emb(torch.full((1, 3, 1), 512).to(DEV))
+    y = dec.inference_vq(got[0].transpose(0, 1).contiguous())
+    assert y.shape == (1, 1, 37 * 40)
+
+
+def test_residual_vq_two_quantizers_matches_oracle():
+    cfg = configs.get_config("tiny")
+    cfg["codec_decoder"]["vq_num_quantizers"] = 2
+    _, dsd = synth.make_state_dicts(cfg)
+    dec = BigCodecDecoder(**cfg["codec_decoder"])
+    dec.load_state_dict(dsd)
+    z = torch.randn(2, 64, 50, generator=gen(9))
+    zq_want, idx_want, loss_want, margin = oracle.quantize(dsd, cfg["codec_decoder"], z)
+    zq, idx, loss = dec.to(DEV)(z.to(DEV), vq=True)
+    assert idx.shape == (2, 2, 50) and loss.shape == (2,)
+    ok = (margin > 1e-5).all(dim=0)
+    assert torch.equal(idx.cpu()[:, ok], idx_want[:, ok])
+    same = (idx.cpu() == idx_want).all(dim=0)
+    assert rel(zq.cpu().permute(0, 2, 1)[same], zq_want.permute(0, 2, 1)[same]) <= TOL
+
+
+def test_indices_to_int16_layout():
+    idx = torch.randint(0, 8192, (2, 91), generator=gen(4), dtype=torch.int32)
+    out = ops.indices_to_int16(idx.to(DEV)).cpu().numpy()
+    assert out.dtype == np.int16 and np.array_equal(out, idx.numpy().T.astype(np.int16))
+
+
+def test_errors_are_exceptions_not_fallbacks():
+    conv = M.WNConv1d(4, 4, kernel_size=3, padding=1).to(DEV)
+    with pytest.raises(ValueError):
+        conv.forward_cl(torch.zeros(1, 10, 5, device=DEV))            # wrong channel count
+    with pytest.raises(TypeError):
+        ops.to_channels_last(torch.zeros(1, 4, 10, device=DEV, dtype=torch.float64))
+    strided = M.WNConv1d(4, 4, kernel_size=10, stride=5, padding=3).to(DEV)
+    with pytest.raises(ValueError):
+        strided.forward_cl(torch.zeros(1, 2, 4, device=DEV))          # too short for the layer

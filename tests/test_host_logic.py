@@ -1,0 +1,168 @@
+"""CPU: host-side logic -- configs, state-dict compatibility, weight packing, sharding."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import REPO
+from audiotokenization_b200 import configs, sharding, synth
+from audiotokenization_b200.vq import BigCodecDecoder, BigCodecEncoder
+from audiotokenization_b200.vq import module as M
+from oracle import bigcodec_oracle as oracle
+
+
+@pytest.mark.parametrize("name", ["tiny", "base", "debug", "debug_causal", "config9_base", "default"])
+@pytest.mark.parametrize("aa", [False, True])
+def test_state_dict_keys_and_shapes_match_reference_layout(name, aa):
+    cfg = configs.get_config(name, antialias=aa)
+    esd, dsd = synth.make_state_dicts(cfg)
+    enc = BigCodecEncoder(**cfg["codec_encoder"])
+    dec = BigCodecDecoder(**cfg["codec_decoder"])
+    enc.load_state_dict(esd, strict=True)
+    dec.load_state_dict(dsd, strict=True)
+    assert list(enc.state_dict()) == list(esd) and list(dec.state_dict()) == list(dsd)
+    if name == "base":  # SURVEY.md Appendix C tensor counts
+        assert (len(esd), len(dsd)) == ((214, 221) if aa else (156, 163))
+        assert tuple(dsd["model.2.block.1.weight_g"].shape) == (512, 1, 1)      # ConvT: per INPUT channel
+        assert tuple(dsd["quantizer.layers.0._codebook.weight"].shape) == (8192, 8)
+    assert int(enc.hop_length) == int(np.prod(cfg["codec_encoder"]["up_ratios"]))
+
+
+def test_yaml_reader_drops_rejected_keys(tmp_path):
+    doc = textwrap.dedent("""
+        codec_encoder: {type: bigcodec, out_channels: 64, ngf: 8, use_rnn: True, rnn_bidirectional: False,
+                        rnn_num_layers: 2, up_ratios: [2, 4, 5], dilations: [1, 3, 9], causal: False, antialias: False}
+        codec_decoder: {in_channels: 64, upsample_initial_channel: 64, ngf: 8, use_rnn: True, rnn_bidirectional: False,
+                        rnn_num_layers: 2, up_ratios: [5, 4, 2], dilations: [1, 3, 9], causal: False, antialias: False,
+                        vq_num_quantizers: 1, vq_dim: 64, vq_commit_weight: 0.25, vq_weight_init: False, fsq: False,
+                        fsq_levels: [4, 4, 4, 8], vq_full_commit_loss: False, codebook_size: 512, codebook_dim: 8}
+        mpd: {periods: [2, 3]}
+    """)
+    p = tmp_path / "m.yaml"
+    p.write_text(doc)
+    cfg = configs.load_model_yaml(str(p))
+    assert "type" not in cfg["codec_encoder"] and "vq_dim" not in cfg["codec_decoder"]
+    BigCodecEncoder(**cfg["codec_encoder"])
+    BigCodecDecoder(**cfg["codec_decoder"])
+    bad = tmp_path / "b.yaml"
+    bad.write_text(doc.replace("type: bigcodec", "type: conformer_stft"))
+    with pytest.raises(ValueError):
+        configs.load_model_yaml(str(bad))
+
+
+def test_conv_weight_packing_is_the_folded_reference_weight():
+    conv = M.WNConv1d(6, 10, kernel_size=7, dilation=3, padding=9)
+    conv.weight_g.data.mul_(1.7)
+    conv.bias.data.normal_()
+    w, b = conv.packed()
+    ref = oracle.fold_weight_norm(conv.weight_g.double(), conv.weight_v.double())
+    assert w.shape == (7, 6, 10)
+    assert torch.allclose(w.permute(2, 1, 0).double(), ref, atol=1e-7)
+    assert conv.out_length(100) == 100
+    # cache invalidates on in-place parameter change
+    conv.weight_g.data.mul_(2.0)
+    conv.weight_g._version  # noqa: B018
+    conv.load_state_dict(conv.state_dict())
+    w2, _ = conv.packed()
+    assert torch.allclose(w2, 2 * w, atol=1e-6)
+
+
+@pytest.mark.parametrize("stride,causal", [(2, False), (4, False), (5, False), (3, True)])
+def test_transposed_conv_phase_packing(stride, causal):
+    cin, cout, T = 5, 4, 9
+    if causal:
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, causal=True)
+        p, conv = 0, m.conv
+    else:
+        p = stride // 2 + stride % 2
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, padding=p, output_padding=stride % 2)
+        conv = m
+    w_ph, b = conv.packed()
+    assert w_ph.shape == (stride, 2, cin, cout)
+    x = torch.randn(2, cin, T, dtype=torch.float64)
+    w = oracle.fold_weight_norm(conv.weight_g.double(), conv.weight_v.double())
+    if causal:
+        ref = F.conv_transpose1d(x, w, conv.bias.double(), stride=stride)[..., :-stride]
+    else:
+        ref = F.conv_transpose1d(x, w, conv.bias.double(), stride=stride, padding=p, output_padding=stride % 2)
+    # emulate bc_convtr1d_fwd's phase loop on the CPU with the packed weights
+    xc = x.transpose(1, 2)
+    y = torch.zeros(2, T * stride, cout, dtype=torch.float64)
+    for ph in range(stride):
+        q = (ph + p) // stride
+        for t in range(T):
+            acc = b.double().expand(2, -1).clone()
+            for k in range(2):
+                g = t + k - (1 - q)
+                if 0 <= g < T:
+                    acc += xc[:, g] @ w_ph[ph, k].double()
+            y[:, t * stride + ph] = acc
+    assert torch.allclose(y.transpose(1, 2), ref, atol=1e-6)
+
+
+def test_unsupported_configurations_are_errors():
+    with pytest.raises(NotImplementedError):
+        M.ResLSTM(32, bidirectional=True)
+    cfg = configs.get_config("tiny")["codec_decoder"]
+    with pytest.raises(NotImplementedError):
+        BigCodecDecoder(**dict(cfg, fsq=True, codebook_size=128))
+    with pytest.raises(ValueError):
+        M.set_precision("fp8")
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 4096, 4099):
+        for w in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    owned = sharding.shard_by_cost([10, 1, 1, 1, 9, 2, 8], 3)
+    assert sorted(i for o in owned for i in o) == list(range(7))
+    loads = [sum([10, 1, 1, 1, 9, 2, 8][i] for i in o) for o in owned]
+    assert max(loads) <= 12
+
+
+def test_two_rank_gloo_shard_and_host_gather(tmp_path):
+    """world_size-2 CPU run of the multi-GPU host logic: each rank takes its shard of a
+    deterministic per-clip 'index' table and rank 0 reassembles it in utterance order."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {REPO!r})
+        import numpy as np, torch, torch.distributed as dist
+        from audiotokenization_b200 import sharding
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        n, tp = 11, 7
+        full = (np.arange(n * tp * 1).reshape(n, tp, 1) % 8192).astype(np.int16)
+        s, e = sharding.shard_range(n, r, w)
+        out = sharding.gather_indices_to_rank0(full[s:e])
+        if r == 0:
+            assert out.dtype == np.int16 and np.array_equal(out, full), "gather mismatch"
+            print("GATHER_OK")
+        else:
+            assert out is None
+        dist.barrier(); dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GATHER_OK" in r.stdout
+
+
+def test_synthetic_inputs_are_deterministic_and_bounded():
+    a = synth.synth_batch(3, 2, 1600)
+    b = synth.synth_batch(3, 2, 1600)
+    assert torch.equal(a, b) and a.abs().max() <= 1.0 and a.std() > 0.1
+    c = synth.fast_synth_batch(5, 4, 1600)
+    assert torch.equal(c, synth.fast_synth_batch(5, 4, 1600)) and c.abs().max() <= 1.0
+    assert not torch.equal(c[0], c[1])
