@@ -262,7 +262,11 @@ extern "C" int bc_convtr1d_fwd(const float* x, const float* w_phases, const floa
   for (int ph = 0; ph < stride; ++ph) {
     const int q = (ph + padding) / stride;  // 0 or 1
     // y[m*stride + ph] = W[j0+stride]^T x[m+q-1] + W[j0]^T x[m+q]
-    const float* wp = w_phases + (size_t)ph * 2 * C_in * C_out;
+    // fp32: [phase][2][C_in][C_out] floats; tensor-core modes: one bc_tc_plan image per phase
+    // (split * 2*C_in*C_out bf16 = split * C_in*C_out float-sized words)
+    const size_t phase_words = precision == BC_PREC_FP32 ? (size_t)2 * C_in * C_out
+                                                         : (size_t)(precision == BC_PREC_BF16X3 ? 2 : 1) * C_in * C_out;
+    const float* wp = w_phases + (size_t)ph * phase_words;
     int rc = bc_conv1d_fwd(x, wp, bias, snake_a, snake_ib, nullptr, y, B, T_in, C_in, T_in, C_out, /*K=*/2,
                            /*stride=*/1, /*dil=*/1, /*pad_left=*/1 - q, /*y_rows=*/T_out, /*y_tstride=*/stride,
                            /*y_toffset=*/ph, flags, precision, s);

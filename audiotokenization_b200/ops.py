@@ -98,11 +98,20 @@ def snake(x: torch.Tensor, a: torch.Tensor, ib: torch.Tensor, antialias: bool = 
 def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int = 1, dilation: int = 1,
            pad_left: int = 0, t_out: int, snake_a: Optional[torch.Tensor] = None,
            snake_ib: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, tanh: bool = False,
-           precision: str = "fp32", out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Dense conv, weights packed ``[K, C_in, C_out]``; see bc_conv1d_fwd."""
+           precision: str = "fp32", out: Optional[torch.Tensor] = None, geometry=None) -> torch.Tensor:
+    """Dense conv.  ``w`` is the fp32 ``[K, C_in, C_out]`` array for precision 'fp32', or the bf16
+    tensor-core image of ``pack_tc_weight`` (then ``geometry=(K, C_in, C_out)`` or the image's own
+    shape gives the sizes); see bc_conv1d_fwd / bc_tc_plan."""
     x = _cl(x)
     B, T_in, C_in = x.shape
-    K, wc_in, C_out = w.shape
+    if geometry is not None:
+        K, wc_in, C_out = geometry
+    elif w.dim() == 3:
+        K, wc_in, C_out = w.shape
+    else:  # [nt, nchunks, split, K, gpc, 2, n_tile, 8]
+        K, wc_in, C_out = w.shape[3], w.shape[1] * w.shape[4] * 16, w.shape[0] * w.shape[6]
+    if (precision == "fp32") != (w.dtype == torch.float32):
+        raise TypeError(f"conv1d: weight dtype {w.dtype} does not match precision {precision!r}")
     if wc_in != C_in:
         raise ValueError(f"conv1d: input has {C_in} channels, weight expects {wc_in}")
     if t_out <= 0:
@@ -124,11 +133,20 @@ def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, st
 
 def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int,
                      padding: int, snake_a: Optional[torch.Tensor] = None, snake_ib: Optional[torch.Tensor] = None,
-                     precision: str = "fp32") -> torch.Tensor:
-    """Transposed conv (k = 2*stride) from phase-packed weights ``[stride, 2, C_in, C_out]``."""
+                     precision: str = "fp32", c_out: Optional[int] = None) -> torch.Tensor:
+    """Transposed conv (k = 2*stride) from phase-packed weights ``[stride, 2, C_in, C_out]`` (fp32) or one
+    tensor-core image per phase (``[stride, <pack_tc_weight image>]``)."""
     x = _cl(x)
     B, T_in, C_in = x.shape
-    s, two, wc_in, C_out = w_phases.shape
+    if (precision == "fp32") != (w_phases.dtype == torch.float32):
+        raise TypeError(f"conv_transpose1d: weight dtype {w_phases.dtype} does not match precision {precision!r}")
+    if precision == "fp32":
+        s, two, wc_in, C_out = w_phases.shape
+    else:
+        img = w_phases.shape[1:]
+        s, two, wc_in, C_out = w_phases.shape[0], img[3], img[1] * img[4] * 16, img[0] * img[6]
+    if c_out is not None and c_out != C_out:
+        raise ValueError("conv_transpose1d: weight does not match c_out")
     if s != stride or two != 2 or wc_in != C_in:
         raise ValueError(f"conv_transpose1d: weight {tuple(w_phases.shape)} does not match stride={stride}, C_in={C_in}")
     y = torch.empty((B, T_in * stride, C_out), device=x.device, dtype=torch.float32)
@@ -139,6 +157,40 @@ def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[tor
                                              stream_ptr(x.device)), "bc_convtr1d_fwd")
     _count(stride)
     return y
+
+
+_TC_PLANS = {}
+
+
+def tc_plan(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision: str):
+    """(n_tile, gpc, nchunks) of the tensor-core tiling, or None when this geometry stays on the fp32 kernel."""
+    if precision == "fp32":
+        return None
+    key = (c_in, c_out, k, stride, dilation, precision)
+    if key not in _TC_PLANS:
+        import ctypes
+        nt, g, nc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        rc = load_library().bc_tc_plan(c_in, c_out, k, stride, dilation, PRECISIONS[precision],
+                                       ctypes.byref(nt), ctypes.byref(g), ctypes.byref(nc))
+        _TC_PLANS[key] = (nt.value, g.value, nc.value) if rc == 0 else None
+    return _TC_PLANS[key]
+
+
+def pack_tc_weight(w_kio: torch.Tensor, plan, precision: str) -> torch.Tensor:
+    """fp32 [K, C_in, C_out] -> the bf16 smem image bc_conv1d_fwd consumes in tensor-core modes
+    ([C_out/n_tile][nchunks][split][K][gpc][2][n_tile][8]; see bc_tc_plan)."""
+    n_tile, gpc, nchunks = plan
+    K, c_in, c_out = w_kio.shape
+    w = w_kio.float()
+    hi = w.to(torch.bfloat16)
+
+    def image(t):
+        return t.reshape(K, nchunks, gpc, 2, 8, c_out // n_tile, n_tile).permute(5, 1, 0, 2, 3, 6, 4)
+
+    parts = [image(hi)]
+    if precision == "bf16x3":
+        parts.append(image((w - hi.float()).to(torch.bfloat16)))
+    return torch.stack(parts, dim=2).contiguous()
 
 
 LSTM_MAX_BATCH = 256

@@ -90,14 +90,29 @@ class _Conv1dWN(_WNParams):
                     self.bias.detach().float().contiguous())
         return self._cached(build)
 
-    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None, res=None, tanh=False):
+    def packed_for(self, precision: str):
+        """(weight image, bias, effective precision): the bf16 tensor-core image when the geometry has a
+        tcgen05 tiling, else the fp32 [k,in,out] array (edge convs stay on the CUDA-core kernel)."""
         w, b = self.packed()
+        plan = ops.tc_plan(self.in_channels, self.out_channels, self.kernel_size, self.stride, self.dilation,
+                           precision)
+        if plan is None:
+            return w, b, "fp32"
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        key = (precision, self._key())
+        if cache.get("key") != key:
+            cache.clear()
+            cache.update(key=key, w=ops.pack_tc_weight(w, plan, precision))
+        return cache["w"], b, precision
+
+    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None, res=None, tanh=False):
+        w, b, prec = self.packed_for(get_precision())
         a = ib = None
         if act is not None:
             a, ib = act.device_params()
         return ops.conv1d(x_cl, w, b, stride=self.stride, dilation=self.dilation, pad_left=self.left_pad,
                           t_out=self.out_length(x_cl.shape[1]), snake_a=a, snake_ib=ib, res=res, tanh=tanh,
-                          precision=get_precision())
+                          precision=prec)
 
     @torch.no_grad()
     def forward(self, x):
@@ -135,13 +150,26 @@ class _ConvTranspose1dWN(_WNParams):
                     self.bias.detach().float().contiguous())
         return self._cached(build)
 
-    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None):
+    def packed_for(self, precision: str):
         w, b = self.packed()
+        plan = ops.tc_plan(self.in_channels, self.out_channels, 2, 1, 1, precision)
+        if plan is None:
+            return w, b, "fp32"
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        key = (precision, self._key())
+        if cache.get("key") != key:
+            cache.clear()
+            cache.update(key=key, w=torch.stack([ops.pack_tc_weight(w[ph], plan, precision)
+                                                 for ph in range(self.stride)]).contiguous())
+        return cache["w"], b, precision
+
+    def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None):
+        w, b, prec = self.packed_for(get_precision())
         a = ib = None
         if act is not None:
             a, ib = act.device_params()
         return ops.conv_transpose1d(x_cl, w, b, stride=self.stride, padding=self.padding, snake_a=a, snake_ib=ib,
-                                    precision=get_precision())
+                                    precision=prec, c_out=self.out_channels)
 
     @torch.no_grad()
     def forward(self, x):
@@ -321,6 +349,18 @@ class _LSTMParams(nn.Module):
             cache[layer] = c
         return c[1:]
 
+    def input_proj_for(self, layer: int, precision: str):
+        """Input-projection weight in the form bc_conv1d_fwd wants for ``precision`` (+ effective precision)."""
+        w_in, bias, _ = self.packed(layer)
+        plan = ops.tc_plan(w_in.shape[1], w_in.shape[2], 1, 1, 1, precision)
+        if plan is None:
+            return w_in, bias, "fp32"
+        cache = self.__dict__.setdefault("_tc_cache", {})
+        key = (layer, precision, w_in.data_ptr())
+        if key not in cache:
+            cache[key] = ops.pack_tc_weight(w_in, plan, precision)
+        return cache[key], bias, precision
+
 
 class ResLSTM(nn.Module):
     """y = LSTM(x^T) + x^T (vq/module.py:143-167); uni-directional only on the hot path."""
@@ -336,8 +376,10 @@ class ResLSTM(nn.Module):
         h = x_cl
         n = self.lstm.num_layers
         for l in range(n):
-            w_in, bias, w_rec = self.lstm.packed(l)
-            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=get_precision())
+            _, _, w_rec = self.lstm.packed(l)
+            w_in, bias, prec = self.lstm.input_proj_for(l, get_precision())
+            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec,
+                             geometry=(1, h.shape[2], 4 * self.lstm.hidden_size))
             h = ops.lstm_recurrent(pre, w_rec, x_cl if (self.skip and l == n - 1) else None)
         return h
 

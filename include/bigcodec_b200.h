@@ -95,6 +95,16 @@ int bc_conv1d_fwd(const float* x, const float* w, const float* bias,
                   int pad_left, int y_rows, int y_tstride, int y_toffset, int flags, int precision,
                   bc_stream_t s);
 
+/* Tensor-core tiling of a conv geometry: n_tile output channels per CTA, gpc 16-channel groups
+ * per staged chunk, nchunks = C_in / (16*gpc).  For precision BC_PREC_BF16 / BC_PREC_BF16X3 the
+ * `w` argument of bc_conv1d_fwd is NOT the fp32 [K][C_in][C_out] array but its bf16 image
+ *   [C_out/n_tile][nchunks][split][K][gpc][2][n_tile][8],  split = 1 (bf16) or 2 (hi, lo = w - hi),
+ * input channel = chunk*16*gpc + g*16 + h*8 + e.  Returns BC_EUNSUPPORTED when the geometry has no
+ * tensor-core tiling (C_in or C_out not a multiple of 16: the 1->C and C->1 edge convs, which stay
+ * on the fp32 kernel). */
+int bc_tc_plan(int C_in, int C_out, int K, int stride, int dilation, int precision,
+               int* n_tile, int* gpc, int* nchunks);
+
 /* Transposed conv as `stride` output phases of 2-tap convs:
  * w_phases[phase][2][C_in][C_out] (host-packed from the folded [C_in,C_out,2*stride]
  * weight: tap0 = W[:,:,j0+stride], tap1 = W[:,:,j0], j0 = (phase+padding) % stride).

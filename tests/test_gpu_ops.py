@@ -254,3 +254,111 @@ def test_errors_are_exceptions_not_fallbacks():
     strided = M.WNConv1d(4, 4, kernel_size=10, stride=5, padding=3).to(DEV)
     with pytest.raises(ValueError):
         strided.forward_cl(torch.zeros(1, 2, 4, device=DEV))          # too short for the layer
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) modes
+# ---------------------------------------------------------------------------------------------
+TC_CASES = [
+    # cin, cout, k, stride, dil, pad, T
+    (32, 32, 7, 1, 1, 3, 777),
+    (32, 32, 7, 1, 9, 27, 300),
+    (64, 64, 7, 1, 3, 9, 1000),
+    (64, 64, 1, 1, 1, 0, 513),
+    (128, 128, 7, 1, 9, 27, 260),
+    (256, 256, 7, 1, 3, 9, 140),
+    (32, 64, 4, 2, 1, 1, 1001),
+    (64, 128, 8, 4, 1, 2, 1000),
+    (128, 256, 10, 5, 1, 3, 999),
+    (256, 512, 10, 5, 1, 3, 400),
+    (512, 512, 3, 1, 1, 1, 80),
+    (512, 2048, 1, 1, 1, 0, 100),
+    (48, 96, 4, 2, 1, 1, 300),
+    (16, 16, 7, 1, 3, 9, 50),
+]
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,pad,T", TC_CASES)
+@pytest.mark.parametrize("precision,fused_act", [("bf16x3", True), ("bf16", False), ("bf16", True), ("bf16x3", False)])
+def test_conv1d_tensor_core_modes(cin, cout, k, stride, dil, pad, T, precision, fused_act):
+    """bf16x3 must be fp32-class (<= 3e-5 vs the float64 oracle); single-pass bf16 is compared with an
+    oracle whose operands are rounded to bf16 the same way (<= 2e-5), and is ~4e-3 from the true result."""
+    g = gen(cin * 7 + cout + k + T)
+    conv = M.WNConv1d(cin, cout, kernel_size=k, stride=stride, dilation=dil, padding=pad)
+    conv.weight_g.data *= torch.exp(torch.randn(cout, 1, 1, generator=g) * 0.2)
+    conv.bias.data = torch.randn(cout, generator=g) * 0.2
+    x = torch.randn(2, cin, T, generator=g)
+    r = torch.randn(2, cout, conv.out_length(T), generator=g)
+    w = oracle.fold_weight_norm(conv.weight_g.double(), conv.weight_v.double())
+    xin = x.double()
+    act = None
+    if fused_act:
+        act = SnakeBeta(cin, alpha_logscale=True)
+        act.alpha.data = torch.randn(cin, generator=g) * 0.3
+        act.beta.data = torch.randn(cin, generator=g) * 0.3
+        xin = oracle.snake_beta(x, act.alpha.data, act.beta.data).double()   # fp32 snake like the kernel
+        act = act.to(DEV)
+    exact = F.conv1d(xin, w, conv.bias.double(), stride=stride, dilation=dil, padding=pad) + r.double()
+    M.set_precision(precision)
+    try:
+        conv = conv.to(DEV)
+        assert conv.packed_for(precision)[2] == precision, "geometry unexpectedly fell back to fp32"
+        got = conv.forward_cl(ops.to_channels_last(x.to(DEV)), act=act,
+                              res=ops.to_channels_last(r.to(DEV))).permute(0, 2, 1)
+    finally:
+        M.set_precision("fp32")
+    assert got.shape == exact.shape
+    if precision == "bf16x3":
+        assert rel(got, exact) <= 3e-5
+    else:
+        emul = F.conv1d(_bf16(xin.float()).double(), _bf16(w.float()).double(), conv.bias.double().cpu(),
+                        stride=stride, dilation=dil, padding=pad) + r.double()
+        assert rel(got, emul) <= 2e-5
+        assert rel(got, exact) <= 1e-2
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_edge_convs_stay_on_fp32_kernel_in_tensor_core_modes(precision):
+    stem = M.WNConv1d(1, 32, kernel_size=7, padding=3).to(DEV)
+    assert stem.packed_for(precision)[2] == "fp32"
+    tail = M.WNConv1d(32, 1, kernel_size=7, padding=3).to(DEV)
+    assert tail.packed_for(precision)[2] == "fp32"
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 3e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("cin,cout,stride,T", [(64, 32, 2, 501), (128, 64, 4, 250), (512, 256, 5, 80)])
+def test_conv_transpose1d_tensor_core_modes(precision, tol, cin, cout, stride, T):
+    g = gen(cin + cout + stride + T)
+    m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, padding=stride // 2 + stride % 2,
+                            output_padding=stride % 2)
+    x = torch.randn(2, cin, T, generator=g)
+    act = SnakeBeta(cin, alpha_logscale=True)
+    act.alpha.data = torch.randn(cin, generator=g) * 0.3
+    act.beta.data = torch.randn(cin, generator=g) * 0.3
+    sd = {n: getattr(m, n).data.clone().double() for n in ("weight_g", "weight_v", "bias")}
+    want = oracle.wn_conv_transpose1d(sd, "", oracle.snake_beta(x, act.alpha.data, act.beta.data).double(),
+                                      stride=stride)
+    M.set_precision(precision)
+    try:
+        got = m.to(DEV).forward_cl(ops.to_channels_last(x.to(DEV)), act=act.to(DEV)).permute(0, 2, 1)
+    finally:
+        M.set_precision("fp32")
+    assert rel(got, want) <= tol
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
+def test_res_lstm_tensor_core_input_projection(precision, tol):
+    m = M.ResLSTM(512, num_layers=2)
+    sd = {"lstm." + k: v.data.clone() for k, v in m.lstm.named_parameters()}
+    x = torch.randn(2, 512, 60, generator=gen(11))
+    want = oracle.res_lstm(sd, "", x, 2)
+    M.set_precision(precision)
+    try:
+        got = m.to(DEV)(x.to(DEV))
+    finally:
+        M.set_precision("fp32")
+    assert rel(got, want) <= tol
