@@ -85,52 +85,77 @@ class BigCodecModel(nn.Module):
         _, idx, margin = self.decoder.quantizer.forward_cl(z_cl, want_margin=want_margin)
         return idx, margin, z_cl
 
-    @torch.no_grad()
-    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8) -> torch.Tensor:
-        """Device waveforms [N,1,T] -> int16 [N,T',n_q] on the device, micro-batched."""
-        outs = []
-        for b0 in range(0, x_dev.shape[0], micro_batch):
-            xb = x_dev[b0:b0 + micro_batch]
-            idx, _, _ = self.encode_indices_cl(xb.reshape(xb.shape[0], xb.shape[2], 1))
-            n_q, B, Tp = idx.shape
-            outs.append(ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q))
-        return torch.cat(outs, dim=0)
+    def _indices_from_features(self, feat):
+        """frame-rate features [B,T',enc_dim] -> int16 [B,T',n_q] on the device."""
+        z_cl = self.encoder.back_cl(feat)
+        _, idx, _ = self.decoder.quantizer.forward_cl(z_cl)
+        n_q, B, Tp = idx.shape
+        return ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
 
     @torch.no_grad()
-    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8) -> np.ndarray:
+    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256) -> torch.Tensor:
+        """Device waveforms [N,1,T] -> int16 [N,T',n_q] on the device.
+
+        Two-stage schedule: the convolutional front end runs in micro-batches (bounded activation
+        memory: the stem's [mb, T, ngf] tensor is the largest), its frame-rate output (2 KB per frame) is
+        collected for up to ``rnn_batch`` utterances, and the sequential LSTM + final conv + VQ then run
+        once over that whole group."""
+        set_precision(self.precision)
+        outs = []
+        N = x_dev.shape[0]
+        for c0 in range(0, N, rnn_batch):
+            c1 = min(N, c0 + rnn_batch)
+            feats = []
+            for b0 in range(c0, c1, micro_batch):
+                xb = x_dev[b0:min(c1, b0 + micro_batch)]
+                feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
+            feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+            del feats
+            outs.append(self._indices_from_features(feat))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256) -> np.ndarray:
         """Host (ideally pinned) float32 waveforms [N,1,T] -> int16 numpy [N,T',n_q].
 
-        Each micro-batch is copied H2D on a side stream while the previous one computes;
-        results come back D2H as int16.  Equal-length clips only (ragged batches are not
-        equivalent to the reference's per-utterance padding)."""
+        Each micro-batch is copied H2D on a side stream while the previous one computes; the int16
+        results of each LSTM group come back D2H asynchronously.  Equal-length clips only (ragged
+        batches are not equivalent to the reference's per-utterance padding)."""
         if wave_host.is_cuda:
             raise ValueError("extract_indices takes HOST waveforms; use indices_device for device tensors")
+        set_precision(self.precision)
         dev = next(self.parameters()).device
         N = wave_host.shape[0]
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         results = []
-        nxt = None
 
-        def stage(b0):
+        def stage(b0, b1):
             with torch.cuda.stream(copy_stream):
-                t = wave_host[b0:b0 + micro_batch].to(dev, non_blocking=True)
+                t = wave_host[b0:b1].to(dev, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             return t, ev
 
-        nxt = stage(0)
-        for b0 in range(0, N, micro_batch):
+        spans = []
+        for c0 in range(0, N, rnn_batch):
+            c1 = min(N, c0 + rnn_batch)
+            spans += [(b0, min(c1, b0 + micro_batch), min(c1, b0 + micro_batch) == c1) for b0 in range(c0, c1, micro_batch)]
+        nxt = stage(spans[0][0], spans[0][1]) if spans else None
+        feats = []
+        for i, (b0, b1, last_of_group) in enumerate(spans):
             xb, ev = nxt
             main.wait_event(ev)
             xb.record_stream(main)
-            if b0 + micro_batch < N:
-                nxt = stage(b0 + micro_batch)
-            idx, _, _ = self.encode_indices_cl(xb.reshape(xb.shape[0], xb.shape[2], 1))
-            n_q, B, Tp = idx.shape
-            i16 = ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
-            host = torch.empty(i16.shape, dtype=torch.int16, pin_memory=True)
-            host.copy_(i16, non_blocking=True)
-            results.append(host)
+            if i + 1 < len(spans):
+                nxt = stage(spans[i + 1][0], spans[i + 1][1])
+            feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
+            if last_of_group:
+                feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+                feats = []
+                i16 = self._indices_from_features(feat)
+                host = torch.empty(i16.shape, dtype=torch.int16, pin_memory=True)
+                host.copy_(i16, non_blocking=True)
+                results.append(host)
         torch.cuda.current_stream(dev).synchronize()
         return np.concatenate([r.numpy() for r in results], axis=0)

@@ -122,7 +122,7 @@ def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, st
         res = _cl(res, "res")
         if tuple(res.shape) != (B, t_out, C_out):
             raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, C_out)}")
-    with _Timed("conv1d", 2.0 * B * t_out * C_out * C_in * K, x.device):
+    with _Timed(("conv1d", C_in, C_out, K, stride, dilation, t_out, B, precision), 2.0 * B * t_out * C_out * C_in * K, x.device):
         check(load_library().bc_conv1d_fwd(ptr(x), ptr(w), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res), ptr(y),
                                            B, T_in, C_in, t_out, C_out, K, stride, dilation, pad_left,
                                            t_out, 1, 0, flags, PRECISIONS[precision], stream_ptr(x.device)),
@@ -151,7 +151,8 @@ def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[tor
         raise ValueError(f"conv_transpose1d: weight {tuple(w_phases.shape)} does not match stride={stride}, C_in={C_in}")
     y = torch.empty((B, T_in * stride, C_out), device=x.device, dtype=torch.float32)
     flags = BC_CONV_SNAKE_IN if snake_a is not None else 0
-    with _Timed("convtr1d", 2.0 * B * T_in * stride * C_out * C_in * 2, x.device):
+    with _Timed(("convtr1d", C_in, C_out, 2 * stride, stride, 1, T_in * stride, B, precision),
+                2.0 * B * T_in * stride * C_out * C_in * 2, x.device):
         check(load_library().bc_convtr1d_fwd(ptr(x), ptr(w_phases), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(y),
                                              B, T_in, C_in, C_out, stride, padding, flags, PRECISIONS[precision],
                                              stream_ptr(x.device)), "bc_convtr1d_fwd")
@@ -208,7 +209,7 @@ def lstm_recurrent(pre: torch.Tensor, w_hh_packed: torch.Tensor, skip: Optional[
     for b0 in range(0, B, LSTM_MAX_BATCH):
         b1 = min(B, b0 + LSTM_MAX_BATCH)
         ws = torch.empty(lib.bc_lstm_workspace_bytes(b1 - b0, H), device=pre.device, dtype=torch.uint8)
-        with _Timed("lstm", 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
+        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, "fp32"), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
             check(lib.bc_lstm_recurrent_fwd(ptr(pre[b0:b1]), ptr(w_hh_packed),
                                             ptr(skip[b0:b1]) if skip is not None else None,
                                             ptr(y[b0:b1]), ptr(ws), b1 - b0, T, H, stream_ptr(pre.device)),

@@ -40,13 +40,31 @@ class BigCodecEncoder(nn.Module):
         self.enc_dim = d_model
         self.eval()
 
+    def _split(self):
+        mods = list(self.block)
+        n_front = len(mods) - 2 - (1 if isinstance(mods[-3], ResLSTM) else 0)
+        return mods[:n_front], mods[n_front:-2], mods[-2], mods[-1]
+
+    def front_cl(self, x_cl):
+        """Conv stem + EncoderBlocks: x_cl [B,T,1] -> frame-rate features [B,T',enc_dim].  This part is
+        independent per utterance AND per time tile, so it is run in small micro-batches."""
+        front, _, _, _ = self._split()
+        h = front[0].forward_cl(x_cl)
+        for m in front[1:]:
+            h = m.forward_cl(h)
+        return h
+
+    def back_cl(self, h):
+        """[ResLSTM] + SnakeBeta + final conv on frame-rate features.  The LSTM is sequential in time, so
+        it is run over as many utterances at once as possible (its cost per step is almost flat in B)."""
+        _, rnn, act, conv = self._split()
+        for m in rnn:
+            h = m.forward_cl(h)
+        return _act_conv(act, conv, h)
+
     def forward_cl(self, x_cl):
         """x_cl [B,T,1] -> latents [B,T',out_channels] (channels-last)."""
-        mods = list(self.block)
-        h = mods[0].forward_cl(x_cl)
-        for m in mods[1:-2]:
-            h = m.forward_cl(h)
-        return _act_conv(mods[-2], mods[-1], h)
+        return self.back_cl(self.front_cl(x_cl))
 
     @torch.no_grad()
     def forward(self, x):

@@ -51,8 +51,10 @@ def parse_args():
     ap.add_argument("--clips-per-gpu", type=int, default=512)
     ap.add_argument("--clip-seconds", type=float, default=30.0)
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("BC_MICRO_BATCH", "8")))
+    ap.add_argument("--rnn-batch", type=int, default=int(os.environ.get("BC_RNN_BATCH", "256")))
     ap.add_argument("--cpu-sample-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write a per-layer timing table (markdown) here")
     return ap.parse_args()
 
 
@@ -177,7 +179,8 @@ def workload_config(args, world, precision):
                         "across 8xB200 (512 clips per GPU, weak scaling)",
             "model": f"BigCodec {args.model} (cfgs/config11/model/base.yaml)" if args.model == "base" else args.model,
             "clips_per_gpu": args.clips_per_gpu, "clip_seconds": args.clip_seconds, "sample_rate": 16000,
-            "global_clips": args.clips_per_gpu * world, "micro_batch": args.micro_batch, "precision": precision,
+            "global_clips": args.clips_per_gpu * world, "micro_batch": args.micro_batch, "rnn_batch": args.rnn_batch,
+            "precision": precision,
             "weights": "random-init, seed 0 (biases / snake alpha,beta / weight-norm gains randomised)",
             "l2_policy": "inputs_larger_than_l2 (983 MB of waveforms per step; every activation tensor > 126 MB)",
             "parallelism": f"utterance-sharded x{world}, no collective on the data path"}
@@ -237,7 +240,7 @@ def main():
     keep = {}
 
     def step_device():
-        keep["idx"] = model.indices_device(x_dev, micro_batch=args.micro_batch)
+        keep["idx"] = model.indices_device(x_dev, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch)
 
     for _ in range(args.warmup):
         step_device()
@@ -252,7 +255,7 @@ def main():
 
     # ---- end to end through the host-buffer API ----------------------------------------------
     def step_e2e():
-        keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch)
+        keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -266,12 +269,20 @@ def main():
     step_device()
     torch.cuda.synchronize(dev)
     prof, ops.PROFILE = ops.PROFILE, None
-    by_kind = {}
-    for kind, flops, a, b in prof:
-        d = by_kind.setdefault(kind, [0.0, 0.0, 0])
-        d[0] += flops
-        d[1] += a.elapsed_time(b)
-        d[2] += 1
+    by_kind, by_layer = {}, {}
+    for key, flops, a, b in prof:
+        ms = a.elapsed_time(b)
+        for table, k in ((by_kind, key[0]), (by_layer, key)):
+            d = table.setdefault(k, [0.0, 0.0, 0])
+            d[0] += flops
+            d[1] += ms
+            d[2] += 1
+    if args.layer_table and rank == 0:
+        with open(args.layer_table, "w") as f:
+            f.write("| kind | C_in | C_out | K | stride | dil | T_out | B | prec | launches | ms/step | TFLOP/s |\n"
+                    "|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
+            for k, (fl, ms, n) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
+                f.write("| " + " | ".join(str(v) for v in k) + f" | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} |\n")
     conv_flops = sum(v[0] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
     conv_ms = sum(v[1] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
     step_ms = ms_total / args.steps
