@@ -31,6 +31,8 @@ _SIGNATURES = {
     "bc_snake_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "bc_conv1d_fwd": (c_int, [c_void_p] * 7 + [c_int] * 14 + [c_void_p]),
     "bc_tc_plan": (c_int, [c_int] * 6 + [POINTER(c_int)] * 3),
+    "bc_resunit_plan": (c_int, [c_int] * 4 + [POINTER(c_int)] * 4),
+    "bc_resunit_fwd": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_void_p]),
     "bc_convtr1d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bc_lstm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bc_lstm_packed_whh_floats": (c_size_t, [c_int]),

@@ -20,13 +20,17 @@
 // Weights arrive pre-packed (host side, once per load) as bf16 blocks in exactly the smem
 // image the kernel needs: [n_tile][chunk][split][tap][group][2 k-planes][N_t][8].
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace {
+using namespace bc::tc;
 
 constexpr int BM = 128;
 constexpr int TC_THREADS = 256;
+#ifndef TC_MIN_CTAS
+#define TC_MIN_CTAS 2
+#endif
 
 struct TcParams {
   const float* x;
@@ -41,83 +45,34 @@ struct TcParams {
   int n_tile, gpc, nchunks, rpp, slab_rows, split, tmem_cols;
   uint32_t idesc;
   int variant;
+  // fused ResidualUnit tail: y = res + W2 * snake2(conv(x) + bias) + bias2   (1x1 conv, C_in == C_out == n_tile)
+  int fuse2;
+  const uint4* w2pk;
+  const float* bias2;
+  const float* sa2;
+  const float* sib2;
+  uint32_t region1_bytes;  // [A slab | B image], re-used for the bf16 intermediate of the fused tail
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr int STAGE_BATCH = 4;  // slab items whose global loads are issued back to back per thread
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int variant) {
-  // cute::UMMA::SmemDescriptor: start [0,14) | LBO [16,30) | SBO [32,46) | version=1 [46,48) | layout_type=0 (no swizzle)
-  if (variant & 1) { uint32_t t = lbo_bytes; lbo_bytes = sbo_bytes; sbo_bytes = t; }
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  if (!(variant & 2)) d |= (uint64_t)1 << 46;
-  return d;
-}
-
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // bounded: a wrong descriptor must surface as a launch failure, never as a hung GPU
-  for (uint32_t it = 0;; ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (it > (1u << 22)) __trap();
-  }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__device__ __forceinline__ void split_store(float v[8], uint4* hi_dst, uint4* lo_dst) {
-  uint4 h;
-  h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
-  h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
-  *hi_dst = h;
-  if (lo_dst) {
-    float r[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) r[e] = v[e] - __bfloat162float(__float2bfloat16_rn(v[e]));
-    uint4 l;
-    l.x = pack_bf16x2(r[0], r[1]); l.y = pack_bf16x2(r[2], r[3]);
-    l.z = pack_bf16x2(r[4], r[5]); l.w = pack_bf16x2(r[6], r[7]);
-    *lo_dst = l;
-  }
-}
-
-__global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const TcParams p) {
+template <int SPLIT, bool FUSE2>
+__global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int planes = 2 * p.gpc;
   const uint32_t plane_bytes = (uint32_t)p.stride * p.rpp * 16u;  // one 8-channel plane of the slab
   const uint32_t a_split_bytes = planes * plane_bytes;
-  const uint32_t a_bytes = a_split_bytes * p.split;
+  const uint32_t a_bytes = a_split_bytes * SPLIT;
   const uint32_t b_split_bytes = (uint32_t)p.K * p.gpc * p.n_tile * 32u;
-  const uint32_t b_bytes = b_split_bytes * p.split;
+  const uint32_t b_bytes = b_split_bytes * SPLIT;
   uint8_t* sA = smem_raw;
   uint8_t* sB = smem_raw + ((a_bytes + 127u) & ~127u);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sB + ((b_bytes + 127u) & ~127u));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint8_t* sB2 = smem_raw + p.region1_bytes;
+  const uint32_t b2_split_bytes = FUSE2 ? (uint32_t)p.n_tile * p.n_tile * 2u : 0u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + ((b2_split_bytes * SPLIT + 127u) & ~127u));
+  const uint32_t mbar = smem_u32(bars), bbar = smem_u32(bars + 1), b2bar = smem_u32(bars + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int b = blockIdx.z;
   const int nt = blockIdx.y;
@@ -126,10 +81,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const TcParams p)
   const float* xb = p.x + (size_t)b * p.T_in * p.C_in;
   const bool snake = (p.flags & BC_CONV_SNAKE_IN) != 0;
 
-  // ---- one-time setup: mbarrier + TMEM allocation ----
+  // ---- one-time setup: mbarriers, TMEM allocation, first weight image in flight ----
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bbar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b2bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    bulk_g2s(smem_u32(sB), p.wpk + (size_t)nt * p.nchunks * (b_bytes / 16), b_bytes, bbar);
+    if (FUSE2) bulk_g2s(smem_u32(sB2), p.w2pk, b2_split_bytes * SPLIT, b2bar);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -140,120 +99,179 @@ __global__ void __launch_bounds__(TC_THREADS) conv1d_tc_kernel(const TcParams p)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  uint32_t phase = 0;
+  uint32_t phase = 0, bphase = 0;
   const int items = planes * p.slab_rows;  // 16-byte slab items per split
+  const int pshift = 31 - __clz(planes);   // planes = 2*gpc is a power of two
+  const int pl = tid & (planes - 1);        // ... and divides the block size: a thread always serves the same plane
   for (int ch = 0; ch < p.nchunks; ++ch) {
     const int ci0 = ch * p.gpc * 16;
     // ---- stage A: x (fp32, HBM) -> snake -> bf16 hi[/lo] -> canonical K-major slab ----
-    for (int i = tid; i < items; i += TC_THREADS) {
-      const int pl = i % planes;
-      const int r = i / planes;
-      const int g = g0 + r;
-      float v[8];
+    float4 a0, a1, b0, b1;
+    if (snake) {
+      a0 = __ldg(reinterpret_cast<const float4*>(p.sa + ci0 + pl * 8));
+      a1 = __ldg(reinterpret_cast<const float4*>(p.sa + ci0 + pl * 8) + 1);
+      b0 = __ldg(reinterpret_cast<const float4*>(p.sib + ci0 + pl * 8));
+      b1 = __ldg(reinterpret_cast<const float4*>(p.sib + ci0 + pl * 8) + 1);
+    }
+    const float* xcol = xb + ci0 + pl * 8;
+    for (int i0 = tid; i0 < items; i0 += TC_THREADS * STAGE_BATCH) {
+      float4 lo4[STAGE_BATCH], hi4[STAGE_BATCH];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (g >= 0 && g < p.T_in) {
-        const float* src = xb + (size_t)g * p.C_in + ci0 + pl * 8;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
-        v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-        if (snake) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.sa + ci0 + pl * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.sa + ci0 + pl * 8) + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.sib + ci0 + pl * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.sib + ci0 + pl * 8) + 1);
-          v[0] = bc::snake_ref(v[0], a0.x, b0.x); v[1] = bc::snake_ref(v[1], a0.y, b0.y);
-          v[2] = bc::snake_ref(v[2], a0.z, b0.z); v[3] = bc::snake_ref(v[3], a0.w, b0.w);
-          v[4] = bc::snake_ref(v[4], a1.x, b1.x); v[5] = bc::snake_ref(v[5], a1.y, b1.y);
-          v[6] = bc::snake_ref(v[6], a1.z, b1.z); v[7] = bc::snake_ref(v[7], a1.w, b1.w);
+      for (int j = 0; j < STAGE_BATCH; ++j) {   // all loads first: STAGE_BATCH x 32 B in flight per thread
+        const int i = i0 + j * TC_THREADS;
+        const int g = g0 + (i >> pshift);
+        if (i < items && g >= 0 && g < p.T_in) {
+          const float4* src = reinterpret_cast<const float4*>(xcol + (size_t)g * p.C_in);
+          lo4[j] = __ldg(src);
+          hi4[j] = __ldg(src + 1);
+        } else {
+          lo4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          hi4[j] = lo4[j];
         }
       }
-      const int ph = r % p.stride, rr = r / p.stride;
-      uint8_t* dst = sA + (size_t)pl * plane_bytes + ((size_t)ph * p.rpp + rr) * 16;
-      split_store(v, reinterpret_cast<uint4*>(dst), p.split == 2 ? reinterpret_cast<uint4*>(dst + a_split_bytes) : nullptr);
-    }
-    // ---- stage B: pre-packed weight image for (n-tile, chunk): straight 16-byte copy ----
-    {
-      const uint4* src = p.wpk + ((size_t)nt * p.nchunks + ch) * (b_bytes / 16);
-      uint4* dst = reinterpret_cast<uint4*>(sB);
-      for (int i = tid; i < (int)(b_bytes / 16); i += TC_THREADS) dst[i] = __ldg(src + i);
+#pragma unroll
+      for (int j = 0; j < STAGE_BATCH; ++j) {
+        const int i = i0 + j * TC_THREADS;
+        if (i < items) {
+          const int r = i >> pshift;
+          float v[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
+          if (snake) snake8<SPLIT>(v, a0, a1, b0, b1);   // snake(0) == 0: padding rows stay zero
+          const int ph = r % p.stride, rr = r / p.stride;
+          split_store<SPLIT>(v, sA + (size_t)pl * plane_bytes + ((size_t)ph * p.rpp + rr) * 16, a_split_bytes);
+        }
+      }
     }
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     // ---- one thread issues every MMA of this chunk, then commits to the mbarrier ----
     if (tid == 0) {
+      mbar_wait(bbar, bphase);   // this chunk's weight image has landed (bulk copy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      const int nterms = p.split == 2 ? 3 : 1;
       for (int k = 0; k < p.K; ++k) {
         const int sh = k * p.dil;
         const uint32_t a_row = ((uint32_t)(sh % p.stride) * p.rpp + (uint32_t)(sh / p.stride)) * 16u;
         for (int g = 0; g < p.gpc; ++g) {
           const uint32_t a_off = (uint32_t)(2 * g) * plane_bytes + a_row;
           const uint32_t b_off = (uint32_t)(k * p.gpc + g) * p.n_tile * 32u;
-          for (int term = 0; term < nterms; ++term) {
+#pragma unroll
+          for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
             // term 0: a_hi*w_hi, 1: a_hi*w_lo, 2: a_lo*w_hi
             const uint32_t aa = a_base + a_off + (term == 2 ? a_split_bytes : 0u);
             const uint32_t bb = b_base + b_off + (term == 1 ? b_split_bytes : 0u);
             const uint64_t ad = make_desc(aa, plane_bytes, 128u, p.variant);
             const uint64_t bd = make_desc(bb, (uint32_t)p.n_tile * 16u, 128u, p.variant);
-            const uint32_t acc = (ch | k | g | term) ? 1u : 0u;
-            mma_bf16(tmem_base, ad, bd, p.idesc, acc);
+            mma_bf16(tmem_base, ad, bd, p.idesc, (ch | k | g | term) ? 1u : 0u);
           }
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
     }
+    bphase ^= 1u;
     // everyone waits until the tensor core has consumed this chunk's smem
-    mbar_wait(smem_u32(mbar), phase);
+    mbar_wait(mbar, phase);
     phase ^= 1u;
+    if (tid == 0 && ch + 1 < p.nchunks)   // next chunk's weights stream in while the slab is being staged
+      bulk_g2s(smem_u32(sB), p.wpk + ((size_t)nt * p.nchunks + ch + 1) * (b_bytes / 16), b_bytes, bbar);
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+  const int q = warp & 3;            // TMEM lane quarter this warp may access
+  const int half = warp >> 2;        // column half
+  const int ncols = p.n_tile / 2;
+  const int col0 = half * ncols;
+  const int t = t0 + q * 32 + lane;
+  const bool row_ok = t < p.T_out;
+  uint32_t acc_col = 0;
+
+  if (FUSE2) {
+    // ---- fused ResidualUnit tail: h = snake2(acc + bias) -> bf16 smem tile -> 1x1 conv on the tensor core ----
+    const uint32_t a2_plane = BM * 16u;
+    const uint32_t a2_split = (uint32_t)(p.n_tile / 8) * a2_plane;
+    uint8_t* sA2 = smem_raw;  // aliases [A | B]: every MMA that read them has completed
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int n8 = min(4, (ncols - c0) / 8);
+      uint32_t r[32];
+      tmem_load(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + c0), n8, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < n8) {
+          const int c = col0 + c0 + 8 * j;
+          const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias + c) + 1);
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.sa2 + c));
+          const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.sa2 + c) + 1);
+          const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.sib2 + c));
+          const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.sib2 + c) + 1);
+          float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
+                        __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
+                        __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
+                        __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+          snake8<SPLIT>(v, s0, s1, i0, i1);
+          split_store<SPLIT>(v, sA2 + (size_t)(c / 8) * a2_plane + (size_t)(q * 32 + lane) * 16, a2_split);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    acc_col = (uint32_t)p.tmem_cols / 2;
+    if (tid == 0) {
+      mbar_wait(b2bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_base = smem_u32(sA2), b_base = smem_u32(sB2);
+      for (int g = 0; g < p.n_tile / 16; ++g) {
+#pragma unroll
+        for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
+          const uint32_t aa = a_base + (uint32_t)(2 * g) * a2_plane + (term == 2 ? a2_split : 0u);
+          const uint32_t bb = b_base + (uint32_t)g * p.n_tile * 32u + (term == 1 ? b2_split_bytes : 0u);
+          mma_bf16(tmem_base + acc_col, make_desc(aa, a2_plane, 128u, p.variant),
+                   make_desc(bb, (uint32_t)p.n_tile * 16u, 128u, p.variant), p.idesc, (g | term) ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    }
+  }
+
   // ---- epilogue: TMEM -> registers -> (+bias, +residual, tanh) -> HBM ----
   {
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = warp >> 2;        // column half
-    const int ncols = p.n_tile / 2;
-    const int col0 = half * ncols;
-    const int t = t0 + q * 32 + lane;
-    const bool row_ok = t < p.T_out;
     const size_t row = (size_t)b * p.y_rows + (size_t)(row_ok ? t : 0) * p.y_tstride + p.y_toffset;
     const int co_base = nt * p.n_tile + col0;
     float* yp = p.y + row * p.C_out + co_base;
     const float* rp = p.res ? p.res + row * p.C_out + co_base : nullptr;
+    const float* bias = FUSE2 ? p.bias2 : p.bias;
     const bool tanh_out = (p.flags & BC_CONV_TANH_OUT) != 0;
-    for (int c = 0; c < ncols; c += 8) {
-      uint32_t r[8];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + c);
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                   : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int n8 = min(4, (ncols - c0) / 8);
+      // residual rows are fetched before the accumulator is touched: their latency overlaps the MMA tail
+      float4 res4[8];
+      if (rp && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < 2 * n8) res4[j] = __ldcs(reinterpret_cast<const float4*>(rp + c0) + j);
+      }
+      if (FUSE2 && c0 == 0) {
+        mbar_wait(mbar, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      uint32_t r[32];
+      tmem_load(tmem_base + acc_col + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + c0), n8, r);
       if (row_ok) {
-        float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[e]);
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + co_base + c));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + co_base + c) + 1);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        for (int j = 0; j < 8; ++j) {
+          if (j < 2 * n8) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co_base + c0) + j);
+              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            }
+            if (rp) { v.x += res4[j].x; v.y += res4[j].y; v.z += res4[j].z; v.w += res4[j].w; }
+            if (tanh_out) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            reinterpret_cast<float4*>(yp + c0)[j] = v;
+          }
         }
-        if (rp) {
-          const float4 r0 = *reinterpret_cast<const float4*>(rp + c);
-          const float4 r1 = *(reinterpret_cast<const float4*>(rp + c) + 1);
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (tanh_out) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
-        }
-        *reinterpret_cast<float4*>(yp + c) = make_float4(v[0], v[1], v[2], v[3]);
-        *(reinterpret_cast<float4*>(yp + c) + 1) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
   }
@@ -293,6 +311,51 @@ int tc_plan(int C_in, int C_out, int K, int stride, int dilation, int precision,
   return BC_OK;
 }
 
+static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
+static int launch_tc(TcParams& p, int precision, cudaStream_t st) {
+  p.split = precision == BC_PREC_BF16X3 ? 2 : 1;
+  p.slab_rows = (BM - 1) * p.stride + (p.K - 1) * p.dil + 1;
+  p.rpp = (p.slab_rows + p.stride - 1) / p.stride;
+  p.tmem_cols = p.fuse2 ? 2 * pow2_cols(p.n_tile) : pow2_cols(p.n_tile);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const char* var = getenv("BC_TC_VARIANT");
+  p.variant = var ? atoi(var) : 0;
+  const size_t a_bytes = (size_t)p.split * 2 * p.gpc * p.stride * p.rpp * 16;
+  const size_t b_bytes = (size_t)p.split * p.K * p.gpc * p.n_tile * 32;
+  size_t region1 = ((a_bytes + 127) & ~size_t(127)) + ((b_bytes + 127) & ~size_t(127));
+  size_t b2 = 0;
+  if (p.fuse2) {
+    const size_t a2 = (size_t)p.split * p.n_tile * BM * 2;   // bf16 intermediate tile(s)
+    if (a2 > region1) region1 = (a2 + 127) & ~size_t(127);
+    b2 = ((size_t)p.split * p.n_tile * p.n_tile * 2 + 127) & ~size_t(127);
+  }
+  p.region1_bytes = (uint32_t)region1;
+  const size_t smem = region1 + b2 + 64;
+  if (smem > 227 * 1024) return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): tile needs %zu B of shared memory", smem);
+  if (p.tmem_cols > 512) return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): %d TMEM columns", p.tmem_cols);
+  if (2 * (size_t)p.gpc * p.stride * p.rpp * 16 >= (1u << 18) || (size_t)p.n_tile * 16 >= (1u << 18))
+    return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): descriptor offset overflow");
+  void (*kern)(const TcParams) = nullptr;
+  int slot = 0;
+  if (p.split == 1 && !p.fuse2) { kern = conv1d_tc_kernel<1, false>; slot = 0; }
+  if (p.split == 2 && !p.fuse2) { kern = conv1d_tc_kernel<2, false>; slot = 1; }
+  if (p.split == 1 && p.fuse2) { kern = conv1d_tc_kernel<1, true>; slot = 2; }
+  if (p.split == 2 && p.fuse2) { kern = conv1d_tc_kernel<2, true>; slot = 3; }
+  static bool configured[64][4] = {{false}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev][slot]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(conv1d_tc)");
+    if (dev >= 0 && dev < 64) configured[dev][slot] = true;
+  }
+  dim3 grid((p.T_out + BM - 1) / BM, p.C_out / p.n_tile, p.B);
+  kern<<<grid, TC_THREADS, smem, st>>>(p);
+  BC_LAUNCH_CHECK("conv1d_tc_kernel");
+  return BC_OK;
+}
+
 int conv1d_tc_fwd(const float* x, const float* w, const float* bias, const float* snake_a, const float* snake_ib,
                   const float* res, float* y, int B, int T_in, int C_in, int T_out, int C_out, int K, int stride,
                   int dilation, int pad_left, int y_rows, int y_tstride, int y_toffset, int flags, int precision,
@@ -307,31 +370,32 @@ int conv1d_tc_fwd(const float* x, const float* w, const float* bias, const float
   p.x = x; p.wpk = reinterpret_cast<const uint4*>(w); p.bias = bias; p.sa = snake_a; p.sib = snake_ib; p.res = res; p.y = y;
   p.B = B; p.T_in = T_in; p.C_in = C_in; p.T_out = T_out; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;
   p.pad_left = pad_left; p.y_rows = y_rows; p.y_tstride = y_tstride; p.y_toffset = y_toffset; p.flags = flags;
-  p.split = precision == BC_PREC_BF16X3 ? 2 : 1;
-  p.slab_rows = (BM - 1) * stride + (K - 1) * dilation + 1;
-  p.rpp = (p.slab_rows + stride - 1) / stride;
-  p.tmem_cols = p.n_tile <= 32 ? 32 : (p.n_tile <= 64 ? 64 : 128);
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  const char* var = getenv("BC_TC_VARIANT");
-  p.variant = var ? atoi(var) : 0;
-  const size_t a_bytes = (size_t)p.split * 2 * p.gpc * stride * p.rpp * 16;
-  const size_t b_bytes = (size_t)p.split * K * p.gpc * p.n_tile * 32;
-  const size_t smem = ((a_bytes + 127) & ~size_t(127)) + ((b_bytes + 127) & ~size_t(127)) + 64;
-  if (smem > 227 * 1024) return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): tile needs %zu B of shared memory", smem);
-  if (2 * (size_t)p.gpc * stride * p.rpp * 16 >= (1u << 18) || (size_t)p.n_tile * 16 >= (1u << 18))
-    return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): descriptor offset overflow");
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(conv1d_tc)");
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
-  dim3 grid((T_out + BM - 1) / BM, C_out / p.n_tile, B);
-  conv1d_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
-  BC_LAUNCH_CHECK("conv1d_tc_kernel");
-  return BC_OK;
+  p.fuse2 = 0; p.w2pk = nullptr; p.bias2 = nullptr; p.sa2 = nullptr; p.sib2 = nullptr;
+  return launch_tc(p, precision, st);
+}
+
+int ru_persist_slots(int C, int K, int dilation, int precision);
+int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
+                        const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
+                        int C, int K, int dilation, int pad_left, int precision, cudaStream_t st);
+
+int resunit_tc_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
+                   const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T, int C,
+                   int K, int dilation, int pad_left, int precision, cudaStream_t st) {
+  if (ru_persist_slots(C, K, dilation, precision) > 0)
+    return resunit_persist_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, st);
+  TcParams p;
+  int rc = tc_plan(C, C, K, 1, dilation, precision, &p.n_tile, &p.gpc, &p.nchunks);
+  if (rc != BC_OK || p.n_tile != C)
+    return fail(BC_EUNSUPPORTED, "resunit(tensor-core): C=%d K=%d has no single-tile tensor-core plan", C, K);
+  if (!aligned16(x) || !aligned16(w7) || !aligned16(w1) || !aligned16(y) || !aligned16(b7) || !aligned16(b1) ||
+      !aligned16(sa1) || !aligned16(sib1) || !aligned16(sa2) || !aligned16(sib2))
+    return fail(BC_EINVAL, "resunit(tensor-core): pointers must be 16-byte aligned");
+  p.x = x; p.wpk = reinterpret_cast<const uint4*>(w7); p.bias = b7; p.sa = sa1; p.sib = sib1; p.res = x; p.y = y;
+  p.B = B; p.T_in = T; p.C_in = C; p.T_out = T; p.C_out = C; p.K = K; p.stride = 1; p.dil = dilation;
+  p.pad_left = pad_left; p.y_rows = T; p.y_tstride = 1; p.y_toffset = 0; p.flags = BC_CONV_SNAKE_IN;
+  p.fuse2 = 1; p.w2pk = reinterpret_cast<const uint4*>(w1); p.bias2 = b1; p.sa2 = sa2; p.sib2 = sib2;
+  return launch_tc(p, precision, st);
 }
 
 }  // namespace bc
@@ -342,4 +406,29 @@ extern "C" int bc_tc_plan(int C_in, int C_out, int K, int stride, int dilation, 
   int rc = bc::tc_plan(C_in, C_out, K, stride, dilation, precision, n_tile, gpc, nchunks);
   if (rc != BC_OK) bc::set_error("tc_plan: geometry C_in=%d C_out=%d K=%d stride=%d dil=%d has no tensor-core tiling", C_in, C_out, K, stride, dilation);
   return rc;
+}
+
+extern "C" int bc_resunit_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
+                              const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B,
+                              int T, int C, int K, int dilation, int pad_left, int precision, bc_stream_t s) {
+  BC_REQUIRE(x && w7 && b7 && sa1 && sib1 && w1 && b1 && sa2 && sib2 && y, "resunit: null pointer");
+  BC_REQUIRE(B > 0 && T > 0 && C > 0 && K > 0 && dilation > 0 && B <= 65535, "resunit: bad shape B=%d T=%d C=%d K=%d", B, T, C, K);
+  BC_REQUIRE(x != y, "resunit: cannot run in place (neighbouring tiles read the input halo)");
+  if (precision == BC_PREC_FP32)
+    return bc::fail(BC_EUNSUPPORTED, "resunit: the fused kernel exists for the tensor-core modes only; chain two bc_conv1d_fwd calls in fp32 mode");
+  return bc::resunit_tc_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, (cudaStream_t)s);
+}
+
+extern "C" int bc_resunit_plan(int C, int K, int dilation, int precision, int* n_tile, int* gpc, int* nchunks,
+                               int* persistent) {
+  if (!n_tile || !gpc || !nchunks || !persistent) return bc::fail(BC_EINVAL, "resunit_plan: null output");
+  if (precision == BC_PREC_FP32) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: tensor-core modes only");
+  if (bc::ru_persist_slots(C, K, dilation, precision) > 0) {
+    *n_tile = C; *gpc = C / 16; *nchunks = 1; *persistent = 1;
+    return BC_OK;
+  }
+  *persistent = 0;
+  int rc = bc::tc_plan(C, C, K, 1, dilation, precision, n_tile, gpc, nchunks);
+  if (rc != BC_OK || *n_tile != C) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: C=%d K=%d has no fused tensor-core plan", C, K);
+  return BC_OK;
 }

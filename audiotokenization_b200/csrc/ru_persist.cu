@@ -1,0 +1,392 @@
+// Persistent, warp-specialised fused ResidualUnit for the high-rate layers (C <= 64), sm_100a.
+//
+//   y = x + W1 * snake2( W7 (*) snake1(x) + b7 ) + b1          (vq/module.py:74-89)
+//
+// One CTA per SM stays resident for the whole launch: both weight images are bulk-copied into shared
+// memory ONCE, then the CTA walks its share of the (item, 128-step) tiles through a 4-stage pipeline
+// whose stages run on different warps and overlap across consecutive tiles:
+//
+//   warps 0-7   LOAD   x (fp32, HBM) -> snake1 -> bf16 hi[/lo] -> K-major slab in smem            (a_full)
+//   warp  8     MMA    conv7: K x C/16 [x3] tcgen05.mma into acc1[s] (TMEM)                         (acc1_full)
+//                      conv1: C/16 [x3] tcgen05.mma on the re-quantised tile into acc2[s]          (acc2_full)
+//   warps 9-16  MID    acc1 -> +b7 -> snake2 -> bf16 hi[/lo] -> smem A2 tile                        (a2_full)
+//   warps 17-20 STORE  acc2 -> +b1 -> +x (residual) -> y (fp32, HBM)
+// The 8 LOAD warps form two groups that take alternate tiles, so the HBM latency of tile i+1 is
+// hidden behind the activation math of tile i.
+//
+// Stage hand-offs are mbarriers; the MMA warp issues conv7 of tile i+1 before conv1 of tile i so the
+// tensor core never waits for the MID stage.  The activation makes exactly one HBM read (plus the
+// L2-resident residual re-read) and one HBM write; the intermediate never leaves the SM.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace {
+using namespace bc::tc;
+
+constexpr int BM = 128;
+constexpr int LOAD_WARPS = 8;
+constexpr int LOAD_THREADS = LOAD_WARPS * 32;
+constexpr int LOAD_GROUPS = 2;                      // loader groups alternate tiles: two tiles' HBM loads in flight
+constexpr int GROUP_WARPS = LOAD_WARPS / LOAD_GROUPS;
+constexpr int GROUP_THREADS = GROUP_WARPS * 32;
+constexpr int MMA_WARP = 8;
+constexpr int MID_WARP0 = 9;                        // 8 warps: 2 per TMEM lane quarter (column halves)
+constexpr int MID_WARPS = 8;
+constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;    // 4 warps
+constexpr int RU_WARPS = EPI_WARP0 + 4;
+constexpr int RU_THREADS = RU_WARPS * 32;
+constexpr int LD_BATCH = 5;
+
+struct RuParams {
+  const float* x;
+  float* y;
+  const uint4* w7;
+  const uint4* w1;
+  const float* b7;
+  const float* b1;
+  const float* sa1;
+  const float* sib1;
+  const float* sa2;
+  const float* sib2;
+  int B, T, C, K, dil, pad_left;
+  int slab_rows, nslot, n_pow2, tiles_per_item, total_tiles;
+  uint32_t idesc;
+};
+
+enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
+       B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
+
+template <int SPLIT>
+__global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C;
+  const int planes = C / 8, groups = C / 16;
+  const uint32_t w7_split = (uint32_t)p.K * C * C * 2u;
+  const uint32_t w1_split = (uint32_t)C * C * 2u;
+  const uint32_t plane_bytes = (uint32_t)p.slab_rows * 16u;
+  const uint32_t a_split = planes * plane_bytes;
+  const uint32_t a_slot = (a_split * SPLIT + 127u) & ~127u;
+  const uint32_t a2_plane = BM * 16u;
+  const uint32_t a2_split = planes * a2_plane;
+  const uint32_t a2_slot = a2_split * SPLIT;
+
+  uint8_t* sW7 = smem_raw;
+  uint8_t* sW1 = sW7 + w7_split * SPLIT;
+  uint8_t* sA = sW1 + w1_split * SPLIT;
+  uint8_t* sA2 = sA + (size_t)a_slot * p.nslot;
+  float* sPar = reinterpret_cast<float*>(sA2 + (size_t)a2_slot * p.nslot);  // b7 | sa2 | sib2 | b1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 4 * C);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
+  const uint32_t bar0 = smem_u32(bars);
+#define BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(B_A_FULL + s), p.nslot == 2 ? GROUP_WARPS : LOAD_WARPS);
+      mbar_init(BAR(B_A_EMPTY + s), 1);
+      mbar_init(BAR(B_ACC1_FULL + s), 1);
+      mbar_init(BAR(B_ACC1_EMPTY + s), MID_WARPS);
+      mbar_init(BAR(B_A2_FULL + s), MID_WARPS);
+      mbar_init(BAR(B_A2_EMPTY + s), 1);
+      mbar_init(BAR(B_ACC2_FULL + s), 1);
+      mbar_init(BAR(B_ACC2_EMPTY + s), 4);
+    }
+    mbar_init(BAR(B_W_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // resident weights: one expect_tx, copies in <= 32 KB pieces
+    const uint32_t w7_bytes = w7_split * SPLIT, w1_bytes = w1_split * SPLIT;
+    mbar_expect_tx(BAR(B_W_FULL), w7_bytes + w1_bytes);
+    for (uint32_t off = 0; off < w7_bytes; off += 32768u)
+      bulk_g2s_notx(smem_u32(sW7) + off, reinterpret_cast<const uint8_t*>(p.w7) + off, min(32768u, w7_bytes - off), BAR(B_W_FULL));
+    for (uint32_t off = 0; off < w1_bytes; off += 32768u)
+      bulk_g2s_notx(smem_u32(sW1) + off, reinterpret_cast<const uint8_t*>(p.w1) + off, min(32768u, w1_bytes - off), BAR(B_W_FULL));
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(4 * p.n_pow2)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < C; i += RU_THREADS) {
+    sPar[i] = __ldg(p.b7 + i);
+    sPar[C + i] = __ldg(p.sa2 + i);
+    sPar[2 * C + i] = __ldg(p.sib2 + i);
+    sPar[3 * C + i] = __ldg(p.b1 + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (warp < LOAD_WARPS) {
+    // ======================= LOAD =======================
+    const int items = planes * p.slab_rows;
+    // two slots: the loader groups take alternate tiles (group g always fills slot g, so a producer is never
+    // more than one mbarrier phase ahead); one slot: all 8 warps stage every tile together
+    const int ngroups = p.nslot == 2 ? LOAD_GROUPS : 1;
+    const int gthreads = LOAD_THREADS / ngroups;
+    const int grp = tid / gthreads;
+    const int gtid = tid - grp * gthreads;
+    const int pshift = 31 - __clz(planes);       // planes is a power of two (C in {16,32,64})
+    const int pl = gtid & (planes - 1);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.sa1 + pl * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.sa1 + pl * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.sib1 + pl * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.sib1 + pl * 8) + 1);
+    int it = grp;
+    for (int tile = first + grp * step; tile < p.total_tiles; tile += ngroups * step, it += ngroups) {
+      const int slot = it % p.nslot, use = it / p.nslot;
+      const int b = tile / p.tiles_per_item;
+      const int g0 = (tile - b * p.tiles_per_item) * BM - p.pad_left;
+      const float* xcol = p.x + (size_t)b * p.T * C + pl * 8;
+      uint8_t* dstA = sA + (size_t)slot * a_slot + (size_t)pl * plane_bytes;
+      bool waited = false;
+      for (int i0 = gtid; i0 < items; i0 += gthreads * LD_BATCH) {
+        float4 lo4[LD_BATCH], hi4[LD_BATCH];
+#pragma unroll
+        for (int j = 0; j < LD_BATCH; ++j) {
+          const int i = i0 + j * gthreads;
+          const int g = g0 + (i >> pshift);
+          if (i < items && g >= 0 && g < p.T) {
+            const float4* src = reinterpret_cast<const float4*>(xcol + (size_t)g * C);
+            lo4[j] = __ldg(src);
+            hi4[j] = __ldg(src + 1);
+          } else {
+            lo4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi4[j] = lo4[j];
+          }
+        }
+        if (!waited) {  // the global loads above are already in flight while we wait for the slot
+          mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+          waited = true;
+        }
+#pragma unroll
+        for (int j = 0; j < LD_BATCH; ++j) {
+          const int i = i0 + j * gthreads;
+          if (i < items) {
+            float v[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
+            snake8<SPLIT>(v, a0, a1, b0, b1);
+            split_store<SPLIT>(v, dstA + (size_t)(i >> pshift) * 16, a_split);
+          }
+        }
+      }
+      if (!waited) mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
+    }
+  } else if (warp == MMA_WARP) {
+    // ======================= MMA issue (one thread) =======================
+    if (lane == 0) {
+      int n_my = 0;
+      for (int tile = first; tile < p.total_tiles; tile += step) ++n_my;
+      mbar_wait(BAR(B_W_FULL), 0);
+      const uint32_t w7_base = smem_u32(sW7), w1_base = smem_u32(sW1);
+      for (int it = 0; it <= n_my; ++it) {
+        if (it < n_my) {  // K-tap conv of tile `it`
+          const int slot = it % p.nslot, use = it / p.nslot, as = it & 1, ause = it >> 1;
+          mbar_wait(BAR(B_A_FULL + slot), (uint32_t)(use & 1));
+          mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + (size_t)slot * a_slot);
+          const uint32_t d = tmem_base + (uint32_t)(as * p.n_pow2);
+          for (int k = 0; k < p.K; ++k) {
+            const uint32_t a_row = (uint32_t)(k * p.dil) * 16u;
+            for (int g = 0; g < groups; ++g) {
+#pragma unroll
+              for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
+                const uint32_t aa = a_base + (uint32_t)(2 * g) * plane_bytes + a_row + (term == 2 ? a_split : 0u);
+                const uint32_t bb = w7_base + (uint32_t)(k * groups + g) * C * 32u + (term == 1 ? w7_split : 0u);
+                mma_bf16(d, make_desc(aa, plane_bytes, 128u), make_desc(bb, (uint32_t)C * 16u, 128u), p.idesc,
+                         (k | g | term) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(BAR(B_A_EMPTY + slot));
+          umma_commit(BAR(B_ACC1_FULL + as));
+        }
+        if (it >= 1) {  // 1x1 conv of tile `it - 1`
+          const int j = it - 1;
+          const int slot = j % p.nslot, use = j / p.nslot, as = j & 1, ause = j >> 1;
+          mbar_wait(BAR(B_A2_FULL + slot), (uint32_t)(use & 1));
+          mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA2 + (size_t)slot * a2_slot);
+          const uint32_t d = tmem_base + (uint32_t)((2 + as) * p.n_pow2);
+          for (int g = 0; g < groups; ++g) {
+#pragma unroll
+            for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
+              const uint32_t aa = a_base + (uint32_t)(2 * g) * a2_plane + (term == 2 ? a2_split : 0u);
+              const uint32_t bb = w1_base + (uint32_t)g * C * 32u + (term == 1 ? w1_split : 0u);
+              mma_bf16(d, make_desc(aa, a2_plane, 128u), make_desc(bb, (uint32_t)C * 16u, 128u), p.idesc,
+                       (g | term) ? 1u : 0u);
+            }
+          }
+          umma_commit(BAR(B_A2_EMPTY + slot));
+          umma_commit(BAR(B_ACC2_FULL + as));
+        }
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    // ======================= MID: acc1 -> snake2 -> bf16 A2 tile =======================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int chalf = (warp - MID_WARP0) >> 2;       // which half of the channels this warp converts
+    const int cbeg = chalf * (C / 2), cend = cbeg + C / 2;
+    int it = 0;
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+      const int slot = it % p.nslot, use = it / p.nslot, as = it & 1, ause = it >> 1;
+      mbar_wait(BAR(B_ACC1_FULL + as), (uint32_t)(ause & 1));
+      tc_fence_after();
+      mbar_wait(BAR(B_A2_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+      uint8_t* dst = sA2 + (size_t)slot * a2_slot + (size_t)row * 16;
+      const uint32_t taddr = tmem_base + (uint32_t)(as * p.n_pow2) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const int n8 = min(4, (cend - c0) / 8);
+        uint32_t r[32];
+        tmem_load(taddr + (uint32_t)c0, n8, r);
+        if (c0 + 32 >= cend) {  // this warp's share of the accumulator is read: hand it back before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_ACC1_EMPTY + as));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < n8) {
+            const int c = c0 + 8 * j;
+            const float4 bi0 = *reinterpret_cast<const float4*>(sPar + c), bi1 = *reinterpret_cast<const float4*>(sPar + c + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(sPar + C + c), s1 = *reinterpret_cast<const float4*>(sPar + C + c + 4);
+            const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * C + c), i1 = *reinterpret_cast<const float4*>(sPar + 2 * C + c + 4);
+            float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
+                          __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
+                          __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
+                          __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+            snake8<SPLIT>(v, s0, s1, i0, i1);
+            split_store<SPLIT>(v, dst + (size_t)(c / 8) * a2_plane, a2_split);
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_A2_FULL + slot));
+    }
+  } else {
+    // ======================= STORE: acc2 + b1 + x -> y =======================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+      const int as = it & 1, ause = it >> 1;
+      const int b = tile / p.tiles_per_item;
+      const int t = (tile - b * p.tiles_per_item) * BM + q * 32 + lane;
+      const bool row_ok = t < p.T;
+      const size_t off = ((size_t)b * p.T + (row_ok ? t : 0)) * C;
+      const float* rp = p.x + off;
+      float* yp = p.y + off;
+      const uint32_t taddr = tmem_base + (uint32_t)((2 + as) * p.n_pow2) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int n8 = min(4, (C - c0) / 8);
+        float4 res4[8];
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < 2 * n8) res4[j] = __ldg(reinterpret_cast<const float4*>(rp + c0) + j);
+        }
+        if (c0 == 0) {
+          mbar_wait(BAR(B_ACC2_FULL + as), (uint32_t)(ause & 1));
+          tc_fence_after();
+        }
+        uint32_t r[32];
+        tmem_load(taddr + (uint32_t)c0, n8, r);
+        if (c0 + 32 >= C) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(B_ACC2_EMPTY + as));
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < 2 * n8) {
+              const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * C + c0 + 4 * j);
+              float4 v;
+              v.x = __uint_as_float(r[4 * j + 0]) + bb.x + res4[j].x;
+              v.y = __uint_as_float(r[4 * j + 1]) + bb.y + res4[j].y;
+              v.z = __uint_as_float(r[4 * j + 2]) + bb.z + res4[j].z;
+              v.w = __uint_as_float(r[4 * j + 3]) + bb.w + res4[j].w;
+              __stcs(reinterpret_cast<float4*>(yp + c0) + j, v);
+            }
+          }
+        }
+      }
+    }
+  }
+#undef BAR
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.n_pow2)) : "memory");
+  }
+}
+
+size_t ru_smem_bytes(int C, int K, int dil, int split, int nslot) {
+  const size_t slab_rows = (BM - 1) + (size_t)(K - 1) * dil + 1;
+  const size_t w = (size_t)split * ((size_t)K * C * C * 2 + (size_t)C * C * 2);
+  const size_t a_slot = ((size_t)split * (C / 8) * slab_rows * 16 + 127) & ~size_t(127);
+  const size_t a2_slot = (size_t)split * (C / 8) * BM * 16;
+  return w + nslot * (a_slot + a2_slot) + 4 * C * sizeof(float) + N_BARS * 8 + 64;
+}
+
+}  // namespace
+
+namespace bc {
+
+// 0 = not applicable, else number of smem operand slots the persistent kernel would use
+int ru_persist_slots(int C, int K, int dilation, int precision) {
+  if (C != 16 && C != 32 && C != 64) return 0;   // power-of-two plane count; weights must stay resident
+  const char* off = getenv("BC_RU_PERSIST");
+  if (off && off[0] == '0') return 0;
+  const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
+  if (ru_smem_bytes(C, K, dilation, split, 2) <= 225 * 1024) return 2;
+  if (ru_smem_bytes(C, K, dilation, split, 1) <= 225 * 1024) return 1;
+  return 0;
+}
+
+int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
+                        const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
+                        int C, int K, int dilation, int pad_left, int precision, cudaStream_t st) {
+  const int nslot = ru_persist_slots(C, K, dilation, precision);
+  if (nslot == 0) return fail(BC_EUNSUPPORTED, "resunit(persistent): C=%d K=%d dil=%d not supported", C, K, dilation);
+  RuParams p;
+  p.x = x; p.y = y; p.w7 = reinterpret_cast<const uint4*>(w7); p.w1 = reinterpret_cast<const uint4*>(w1);
+  p.b7 = b7; p.b1 = b1; p.sa1 = sa1; p.sib1 = sib1; p.sa2 = sa2; p.sib2 = sib2;
+  p.B = B; p.T = T; p.C = C; p.K = K; p.dil = dilation; p.pad_left = pad_left;
+  p.slab_rows = (BM - 1) + (K - 1) * dilation + 1;
+  p.nslot = nslot;
+  p.n_pow2 = C <= 32 ? 32 : 64;
+  p.tiles_per_item = (T + BM - 1) / BM;
+  const long long total = (long long)p.tiles_per_item * B;
+  if (total > 2147483647ll) return fail(BC_EINVAL, "resunit(persistent): too many tiles");
+  p.total_tiles = (int)total;
+  p.idesc = idesc_bf16_m128(C);
+  const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
+  const size_t smem = ru_smem_bytes(C, K, dilation, split, nslot);
+  if ((size_t)p.slab_rows * 16 * 2 >= (1u << 18)) return fail(BC_EUNSUPPORTED, "resunit(persistent): descriptor offset overflow");
+  void (*kern)(const RuParams) = split == 2 ? ru_persist_kernel<2> : ru_persist_kernel<1>;
+  static bool configured[64][2] = {{false}};
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 0 || dev >= 64 || !configured[dev][split - 1]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(ru_persist)");
+    if (dev >= 0 && dev < 64) configured[dev][split - 1] = true;
+  }
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  kern<<<grid, RU_THREADS, smem, st>>>(p);
+  BC_LAUNCH_CHECK("ru_persist_kernel");
+  return BC_OK;
+}
+
+}  // namespace bc

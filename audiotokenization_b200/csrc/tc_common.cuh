@@ -1,0 +1,157 @@
+// Device-side building blocks shared by the tcgen05 kernels (sm_100a): shared-memory matrix descriptors,
+// MMA issue, mbarrier waits, bulk async copies, bf16 hi/lo splitting, TMEM loads.
+// Bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS 4.x, vendored in the image) -- third-party
+// documentation of the hardware formats, not the reference repository.
+#pragma once
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace bc {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int variant = 0) {
+  // cute::UMMA::SmemDescriptor: start [0,14) | LBO [16,30) | SBO [32,46) | version=1 [46,48) | layout_type=0 (no swizzle)
+  if (variant & 1) { uint32_t t = lbo_bytes; lbo_bytes = sbo_bytes; sbo_bytes = t; }
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  if (!(variant & 2)) d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~1 ms
+  // passes) instead of burning issue slots in a spin loop.  Bounded: a wrong descriptor or a broken
+  // pipeline must surface as a launch failure, never as a hung GPU.
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) return;
+    if (it > 4000u) __trap();
+  }
+}
+
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int SPLIT>
+__device__ __forceinline__ void split_store(const float v[8], uint8_t* dst, uint32_t lo_offset) {
+  uint4 h;
+  h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+  h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = h;
+  if (SPLIT == 2) {
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = v[e] - __bfloat162float(__float2bfloat16_rn(v[e]));
+    uint4 l;
+    l.x = pack_bf16x2(r[0], r[1]); l.y = pack_bf16x2(r[2], r[3]);
+    l.z = pack_bf16x2(r[4], r[5]); l.w = pack_bf16x2(r[6], r[7]);
+    *reinterpret_cast<uint4*>(dst + lo_offset) = l;
+  }
+}
+
+// SnakeBeta with an explicit range reduction to [-pi/2, pi/2] followed by the SFU sine: sin^2 is
+// pi-periodic, so the quadrant never matters.  |error| ~ 4e-7 absolute, independent of |x*a|.
+__device__ __forceinline__ float snake_tc(float x, float a, float ib) {
+  const float t = x * a;
+  // round-to-nearest via the 1.5*2^23 trick (FMA pipe) instead of FRND (SFU pipe); |t/pi| < 2^22 always here
+  const float n = __fadd_rn(__fmaf_rn(t, 0.318309886183790672f, 12582912.f), -12582912.f);
+  float r = fmaf(n, -3.14159274101257324f, t);
+  r = fmaf(n, 8.74227765734758577e-8f, r);   // pi - float(pi) = -8.742e-8
+  const float s = __sinf(r);
+  return fmaf(ib, s * s, x);
+}
+
+// single-pass bf16 mode: the operand is rounded to 8 mantissa bits right after, so the SFU sine on the raw
+// product is plenty (its error grows like |x*a| * 6e-8, three orders below the bf16 rounding).
+__device__ __forceinline__ float snake_bf(float x, float a, float ib) {
+  const float s = __sinf(x * a);
+  return fmaf(ib, s * s, x);
+}
+
+template <int SPLIT>
+__device__ __forceinline__ void snake8(float v[8], const float4& a0, const float4& a1, const float4& b0, const float4& b1) {
+  if (SPLIT == 2) {
+    v[0] = snake_tc(v[0], a0.x, b0.x); v[1] = snake_tc(v[1], a0.y, b0.y);
+    v[2] = snake_tc(v[2], a0.z, b0.z); v[3] = snake_tc(v[3], a0.w, b0.w);
+    v[4] = snake_tc(v[4], a1.x, b1.x); v[5] = snake_tc(v[5], a1.y, b1.y);
+    v[6] = snake_tc(v[6], a1.z, b1.z); v[7] = snake_tc(v[7], a1.w, b1.w);
+  } else {
+    v[0] = snake_bf(v[0], a0.x, b0.x); v[1] = snake_bf(v[1], a0.y, b0.y);
+    v[2] = snake_bf(v[2], a0.z, b0.z); v[3] = snake_bf(v[3], a0.w, b0.w);
+    v[4] = snake_bf(v[4], a1.x, b1.x); v[5] = snake_bf(v[5], a1.y, b1.y);
+    v[6] = snake_bf(v[6], a1.z, b1.z); v[7] = snake_bf(v[7], a1.w, b1.w);
+  }
+}
+
+// accumulator columns [c0, c0 + 8*n8) of this thread's TMEM lane -> r[]   (n8 <= 4, warp-uniform)
+__device__ __forceinline__ void tmem_load(uint32_t taddr, int n8, uint32_t r[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < n8) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[8 * j + 0]), "=r"(r[8 * j + 1]), "=r"(r[8 * j + 2]), "=r"(r[8 * j + 3]), "=r"(r[8 * j + 4]),
+                     "=r"(r[8 * j + 5]), "=r"(r[8 * j + 6]), "=r"(r[8 * j + 7])
+                   : "r"(taddr + 8u * j));
+    }
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_notx(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128
+__host__ __device__ inline uint32_t idesc_bf16_m128(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+}  // namespace tc
+}  // namespace bc

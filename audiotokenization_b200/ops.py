@@ -131,6 +131,21 @@ def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, st
     return y
 
 
+def resunit(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, b1, sa2, sib2, *, k: int,
+            dilation: int, pad_left: int, precision: str) -> torch.Tensor:
+    """Fused ResidualUnit (tensor-core modes): y = x + W1 snake2(W7 * snake1(x) + b7) + b1."""
+    x = _cl(x)
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    flops = 2.0 * B * T * C * C * (k + 1)
+    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device):
+        check(load_library().bc_resunit_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1), ptr(sa2),
+                                            ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left, PRECISIONS[precision],
+                                            stream_ptr(x.device)), "bc_resunit_fwd")
+    _count()
+    return y
+
+
 def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[torch.Tensor], *, stride: int,
                      padding: int, snake_a: Optional[torch.Tensor] = None, snake_ib: Optional[torch.Tensor] = None,
                      precision: str = "fp32", c_out: Optional[int] = None) -> torch.Tensor:
@@ -174,6 +189,20 @@ def tc_plan(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision
         rc = load_library().bc_tc_plan(c_in, c_out, k, stride, dilation, PRECISIONS[precision],
                                        ctypes.byref(nt), ctypes.byref(g), ctypes.byref(nc))
         _TC_PLANS[key] = (nt.value, g.value, nc.value) if rc == 0 else None
+    return _TC_PLANS[key]
+
+
+def resunit_plan(c: int, k: int, dilation: int, precision: str):
+    """((n_tile, gpc, nchunks) of the W7 image, persistent?) for the fused ResidualUnit kernel, or None."""
+    if precision == "fp32":
+        return None
+    key = ("ru", c, k, dilation, precision)
+    if key not in _TC_PLANS:
+        import ctypes
+        nt, g, nc, pers = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        rc = load_library().bc_resunit_plan(c, k, dilation, PRECISIONS[precision], ctypes.byref(nt), ctypes.byref(g),
+                                            ctypes.byref(nc), ctypes.byref(pers))
+        _TC_PLANS[key] = ((nt.value, g.value, nc.value), bool(pers.value)) if rc == 0 else None
     return _TC_PLANS[key]
 
 

@@ -22,6 +22,7 @@ from . import activations
 from .alias_free_torch import Activation1d
 
 _PRECISION = ["fp32"]
+FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 
 
 def set_precision(mode: str) -> None:
@@ -249,9 +250,35 @@ class ResidualUnit(nn.Module):
             WNConv1d(dim, dim, kernel_size=1),
         )
 
+    def _fused_plan(self, precision):
+        """Geometry of the one-kernel path, or None (fp32 mode, anti-aliased activations, C > 128, ...)."""
+        if precision == "fp32" or not FUSE_RESUNIT[0] or self.block[0].antialias:
+            return None
+        conv7 = self.block[1].conv if isinstance(self.block[1], CausalConv1d) else self.block[1]
+        conv1 = self.block[3]
+        C = conv7.in_channels
+        plan = ops.resunit_plan(C, conv7.kernel_size, conv7.dilation, precision)
+        if plan is None:
+            return None
+        return conv7, conv1, plan[0], (C, C // 16, 1)
+
     def forward_cl(self, x_cl):
-        h = _act_conv(self.block[0], self.block[1], x_cl)
-        return _act_conv(self.block[2], self.block[3], h, res=x_cl)
+        prec = get_precision()
+        fused = self._fused_plan(prec)
+        if fused is None:
+            h = _act_conv(self.block[0], self.block[1], x_cl)
+            return _act_conv(self.block[2], self.block[3], h, res=x_cl)
+        conv7, conv1, plan7, plan1 = fused
+        cache = self.__dict__.setdefault("_ru_cache", {})
+        key = (prec, plan7, conv7._key(), conv1._key())
+        if cache.get("key") != key:
+            cache.clear()
+            cache.update(key=key, w7=ops.pack_tc_weight(conv7.packed()[0], plan7, prec),
+                         w1=ops.pack_tc_weight(conv1.packed()[0], plan1, prec))
+        sa1, sib1 = self.block[0].act.device_params()
+        sa2, sib2 = self.block[2].act.device_params()
+        return ops.resunit(x_cl, cache["w7"], conv7.packed()[1], sa1, sib1, cache["w1"], conv1.packed()[1], sa2, sib2,
+                           k=conv7.kernel_size, dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec)
 
     @torch.no_grad()
     def forward(self, x):

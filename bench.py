@@ -283,16 +283,17 @@ def main():
                     "|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
             for k, (fl, ms, n) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
                 f.write("| " + " | ".join(str(v) for v in k) + f" | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} |\n")
-    conv_flops = sum(v[0] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
-    conv_ms = sum(v[1] for k, v in by_kind.items() if k in ("conv1d", "convtr1d"))
+    CONV_KINDS = ("conv1d", "convtr1d", "resunit")
+    conv_flops = sum(v[0] for k, v in by_kind.items() if k in CONV_KINDS)
+    conv_ms = sum(v[1] for k, v in by_kind.items() if k in CONV_KINDS)
     step_ms = ms_total / args.steps
     peaks = load_peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv1d (dense contractions incl. LSTM input projection)",
+    roofline = {"bound": "tensor", "kernel": "conv1d / fused ResidualUnit (dense contractions incl. LSTM input projection)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                "launches_per_step": sum(v[2] for k, v in by_kind.items() if k in ("conv1d", "convtr1d")),
+                "launches_per_step": sum(v[2] for k, v in by_kind.items() if k in CONV_KINDS),
                 "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms if step_ms else None,
                 "lstm_ms_per_step": by_kind.get("lstm", [0, 0, 0])[1],
                 "whole_step_frac": (value / world) * ENC_GFLOP_PER_AUDIO_S.get(args.model, 0.0) / 1e3

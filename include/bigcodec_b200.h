@@ -105,6 +105,22 @@ int bc_conv1d_fwd(const float* x, const float* w, const float* bias,
 int bc_tc_plan(int C_in, int C_out, int K, int stride, int dilation, int precision,
                int* n_tile, int* gpc, int* nchunks);
 
+/* Fused ResidualUnit (vq/module.py:74-89) for the tensor-core modes, one kernel, one HBM read and one
+ * write of the activation:
+ *   y = x + W1 * snake2( W7 (*) snake1(x) + b7 ) + b1
+ * W7: dilated K-tap "same" conv C->C (image per bc_tc_plan(C, C, K, 1, dilation)), W1: 1x1 conv C->C
+ * (image per bc_tc_plan with n_tile = C, gpc = C/16, nchunks = 1).  The K-tap accumulator stays in TMEM,
+ * is activated and re-quantised to bf16 in shared memory and feeds the second MMA chain directly.
+ * Needs C % 16 == 0 and C <= 128 (one accumulator tile); otherwise BC_EUNSUPPORTED (callers chain two
+ * bc_conv1d_fwd calls).  pad_left = dilation*(K-1)/2 (or dilation*(K-1) for the causal variant). */
+/* Weight-image geometry bc_resunit_fwd expects for W7 (same meaning as bc_tc_plan; W1 is always
+ * n_tile = C, gpc = C/16, nchunks = 1).  *persistent = 1 when the persistent warp-specialised kernel
+ * (weights resident in shared memory, C in {16,32,64}) will run, 0 for the per-tile kernel. */
+int bc_resunit_plan(int C, int K, int dilation, int precision, int* n_tile, int* gpc, int* nchunks, int* persistent);
+int bc_resunit_fwd(const float* x, const float* w7, const float* b7, const float* snake1_a, const float* snake1_ib,
+                   const float* w1, const float* b1, const float* snake2_a, const float* snake2_ib, float* y,
+                   int B, int T, int C, int K, int dilation, int pad_left, int precision, bc_stream_t s);
+
 /* Transposed conv as `stride` output phases of 2-tap convs:
  * w_phases[phase][2][C_in][C_out] (host-packed from the folded [C_in,C_out,2*stride]
  * weight: tap0 = W[:,:,j0+stride], tap1 = W[:,:,j0], j0 = (phase+padding) % stride).

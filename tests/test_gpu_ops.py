@@ -362,3 +362,39 @@ def test_res_lstm_tensor_core_input_projection(precision, tol):
     finally:
         M.set_precision("fp32")
     assert rel(got, want) <= tol
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 5e-5), ("bf16", 1.5e-2)])
+@pytest.mark.parametrize("C,dil,causal,T", [(32, 1, False, 1000), (32, 9, False, 300), (64, 3, False, 777),
+                                            (128, 9, False, 260), (64, 9, False, 30), (16, 3, True, 333),
+                                            (48, 1, False, 200), (96, 3, False, 150)])
+def test_fused_residual_unit_matches_oracle(precision, tol, C, dil, causal, T):
+    """One-kernel ResidualUnit (conv7 -> snake -> conv1 -> +x, intermediate kept in TMEM/smem) against the
+    float64 oracle, and against the unfused two-kernel path of the same precision."""
+    g = gen(C + dil + T)
+    ru = M.ResidualUnit(C, dilation=dil, causal=causal)
+    sd = {}
+    for name, prm in ru.named_parameters():
+        if name.endswith(("alpha", "beta")):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.3
+        elif name.endswith("bias"):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.2
+        elif name.endswith("weight_g"):
+            prm.data = prm.data * torch.exp(torch.randn(prm.shape, generator=g) * 0.2)
+    for name, prm in ru.named_parameters():
+        sd[name] = prm.data.clone().double()
+    x = torch.randn(2, C, T, generator=g)
+    want = oracle.residual_unit(sd, "", x.double(), dil, causal, False)
+    ru = ru.to(DEV)
+    M.set_precision(precision)
+    try:
+        assert ru._fused_plan(precision) is not None
+        got = ru(x.to(DEV))
+        M.FUSE_RESUNIT[0] = False
+        unfused = ru(x.to(DEV))
+    finally:
+        M.FUSE_RESUNIT[0] = True
+        M.set_precision("fp32")
+    assert got.shape == want.shape
+    assert rel(got, want) <= tol
+    assert rel(got, unfused) <= tol
