@@ -38,8 +38,13 @@ _SIGNATURES = {
     "bc_lstm_packed_whh_floats": (c_size_t, [c_int]),
     "bc_lstm_pack_whh": (c_int, [c_void_p, c_void_p, c_int]),
     "bc_lstm_recurrent_fwd": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    "bc_lstm_tc_slice_cols": (c_int, [c_int]),
+    "bc_lstm_tc_max_batch": (c_int, [c_int, c_int]),
+    "bc_lstm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "bc_lstm_tc_recurrent_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "bc_vq_encode": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "bc_debug_set_ru_trace": (c_int, [c_void_p]),
     "bc_indices_to_int16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 

@@ -52,7 +52,10 @@ struct RuParams {
   int B, T, C, K, dil, pad_left;
   int slab_rows, nslot, n_pow2, tiles_per_item, total_tiles;
   uint32_t idesc;
+  long long* trace;   // debug: [tile_it < 64][16 events] clock64 stamps of CTA 0 (NULL = off)
 };
+
+#define TRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
 
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
        B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       const float* xcol = p.x + (size_t)b * p.T * C + pl * 8;
       uint8_t* dstA = sA + (size_t)slot * a_slot + (size_t)pl * plane_bytes;
       bool waited = false;
+      if (gtid == 0) TRACE(0);
       for (int i0 = gtid; i0 < items; i0 += gthreads * LD_BATCH) {
         float4 lo4[LD_BATCH], hi4[LD_BATCH];
 #pragma unroll
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
         if (!waited) {  // the global loads above are already in flight while we wait for the slot
           mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
           waited = true;
+          if (gtid == 0) TRACE(1);
         }
 #pragma unroll
         for (int j = 0; j < LD_BATCH; ++j) {
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       if (!waited) mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
       fence_async_smem();
       __syncwarp();
+      if (gtid == 0) TRACE(2);
       if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
     }
   } else if (warp == MMA_WARP) {
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_A_FULL + slot), (uint32_t)(use & 1));
           mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
+          TRACE(3);
           const uint32_t a_base = smem_u32(sA + (size_t)slot * a_slot);
           const uint32_t d = tmem_base + (uint32_t)(as * p.n_pow2);
           for (int k = 0; k < p.K; ++k) {
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           }
           umma_commit(BAR(B_A_EMPTY + slot));
           umma_commit(BAR(B_ACC1_FULL + as));
+          TRACE(4);
         }
         if (it >= 1) {  // 1x1 conv of tile `it - 1`
           const int j = it - 1;
@@ -213,6 +221,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_A2_FULL + slot), (uint32_t)(use & 1));
           mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
+          { const int it = j; TRACE(5); }
           const uint32_t a_base = smem_u32(sA2 + (size_t)slot * a2_slot);
           const uint32_t d = tmem_base + (uint32_t)((2 + as) * p.n_pow2);
           for (int g = 0; g < groups; ++g) {
@@ -226,6 +235,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           }
           umma_commit(BAR(B_A2_EMPTY + slot));
           umma_commit(BAR(B_ACC2_FULL + as));
+          { const int it = j; TRACE(6); }
         }
       }
     }
@@ -241,6 +251,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       mbar_wait(BAR(B_ACC1_FULL + as), (uint32_t)(ause & 1));
       tc_fence_after();
       mbar_wait(BAR(B_A2_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+      if (warp == MID_WARP0) TRACE(7);
       uint8_t* dst = sA2 + (size_t)slot * a2_slot + (size_t)row * 16;
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.n_pow2) + ((uint32_t)(q * 32) << 16);
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       }
       fence_async_smem();
       __syncwarp();
+      if (warp == MID_WARP0) TRACE(8);
       if (lane == 0) mbar_arrive(BAR(B_A2_FULL + slot));
     }
   } else {
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       const float* rp = p.x + off;
       float* yp = p.y + off;
       const uint32_t taddr = tmem_base + (uint32_t)((2 + as) * p.n_pow2) + ((uint32_t)(q * 32) << 16);
+      if (warp == EPI_WARP0) TRACE(9);
       for (int c0 = 0; c0 < C; c0 += 32) {
         const int n8 = min(4, (C - c0) / 8);
         float4 res4[8];
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
         if (c0 == 0) {
           mbar_wait(BAR(B_ACC2_FULL + as), (uint32_t)(ause & 1));
           tc_fence_after();
+          if (warp == EPI_WARP0) TRACE(10);
         }
         uint32_t r[32];
         tmem_load(taddr + (uint32_t)c0, n8, r);
@@ -319,6 +333,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           }
         }
       }
+      if (warp == EPI_WARP0) TRACE(11);
     }
   }
 #undef BAR
@@ -341,6 +356,8 @@ size_t ru_smem_bytes(int C, int K, int dil, int split, int nslot) {
 }  // namespace
 
 namespace bc {
+
+static long long* g_ru_trace = nullptr;
 
 // 0 = not applicable, else number of smem operand slots the persistent kernel would use
 int ru_persist_slots(int C, int K, int dilation, int precision) {
@@ -370,6 +387,7 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
   if (total > 2147483647ll) return fail(BC_EINVAL, "resunit(persistent): too many tiles");
   p.total_tiles = (int)total;
   p.idesc = idesc_bf16_m128(C);
+  p.trace = g_ru_trace;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
   const size_t smem = ru_smem_bytes(C, K, dilation, split, nslot);
   if ((size_t)p.slab_rows * 16 * 2 >= (1u << 18)) return fail(BC_EUNSUPPORTED, "resunit(persistent): descriptor offset overflow");
@@ -390,3 +408,9 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
 }
 
 }  // namespace bc
+
+// debug hook (not part of the product path): device buffer of 64*16 int64 that receives clock64 stamps
+extern "C" int bc_debug_set_ru_trace(void* device_buffer) {
+  bc::g_ru_trace = reinterpret_cast<long long*>(device_buffer);
+  return BC_OK;
+}

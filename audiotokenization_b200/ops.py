@@ -247,6 +247,53 @@ def lstm_recurrent(pre: torch.Tensor, w_hh_packed: torch.Tensor, skip: Optional[
     return y
 
 
+def lstm_tc_max_batch(H: int, precision: str) -> int:
+    """Largest batch one tensor-core LSTM launch takes (0: no tensor-core plan for this H / precision)."""
+    if precision == "fp32":
+        return 0
+    return int(load_library().bc_lstm_tc_max_batch(H, PRECISIONS[precision]))
+
+
+def pack_lstm_tc_weight(w_hh: torch.Tensor, precision: str) -> torch.Tensor:
+    """W_hh [4H, H] fp32 -> bf16 image [4H/NS][split][H/16][2][NS][8] of bc_lstm_tc_recurrent_fwd."""
+    NS = int(load_library().bc_lstm_tc_slice_cols(PRECISIONS[precision]))
+    H = w_hh.shape[1]
+    U = NS // 4
+    w = w_hh.float().view(4, H // U, U, H).permute(1, 0, 2, 3).reshape(4 * H // NS, NS, H)
+    hi = w.to(torch.bfloat16)
+
+    def image(t):   # [S, NS, H] -> [S, H/16, 2, NS, 8]
+        return t.reshape(-1, NS, H // 16, 2, 8).permute(0, 2, 3, 1, 4)
+
+    parts = [image(hi)]
+    if precision == "bf16x3":
+        parts.append(image((w - hi.float()).to(torch.bfloat16)))
+    return torch.stack(parts, dim=1).contiguous()
+
+
+def lstm_recurrent_tc(pre: torch.Tensor, w_image: torch.Tensor, skip: Optional[torch.Tensor], precision: str,
+                      max_batch: int) -> torch.Tensor:
+    """Tensor-core recurrence; ``pre`` = [B,T,4H] input projection (+ both biases)."""
+    pre = _cl(pre, "pre")
+    B, T, H4 = pre.shape
+    H = H4 // 4
+    lib = load_library()
+    y = torch.empty((B, T, H), device=pre.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _cl(skip, "skip")
+    for b0 in range(0, B, max_batch):
+        b1 = min(B, b0 + max_batch)
+        ws = torch.empty(lib.bc_lstm_tc_workspace_bytes(b1 - b0, H, PRECISIONS[precision]), device=pre.device,
+                         dtype=torch.uint8)
+        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, precision), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
+            check(lib.bc_lstm_tc_recurrent_fwd(ptr(pre[b0:b1]), ptr(w_image),
+                                               ptr(skip[b0:b1]) if skip is not None else None, ptr(y[b0:b1]), ptr(ws),
+                                               b1 - b0, T, H, PRECISIONS[precision], stream_ptr(pre.device)),
+                  "bc_lstm_tc_recurrent_fwd")
+        _count()
+    return y
+
+
 def vq_encode(z: torch.Tensor, w_in: Optional[torch.Tensor], b_in: Optional[torch.Tensor], cb_norm: torch.Tensor,
               want_margin: bool = False, want_ze: bool = False):
     """z [N,C] -> (idx int32 [N], margin [N] | None, z_e [N,D] | None)."""

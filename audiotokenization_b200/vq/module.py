@@ -22,6 +22,7 @@ from . import activations
 from .alias_free_torch import Activation1d
 
 _PRECISION = ["fp32"]
+LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 
 
@@ -376,6 +377,17 @@ class _LSTMParams(nn.Module):
             cache[layer] = c
         return c[1:]
 
+    def recurrent_image_for(self, layer: int, precision: str):
+        """W_hh as the bf16 image of the tensor-core recurrence kernel."""
+        w_hh = getattr(self, f"weight_hh_l{layer}")
+        cache = self.__dict__.setdefault("_rec_cache", {})
+        key = (layer, precision)
+        ver = (w_hh._version, w_hh.data_ptr())
+        if key not in cache or cache[key][0] != ver:
+            with torch.no_grad():
+                cache[key] = (ver, ops.pack_lstm_tc_weight(w_hh.detach(), precision))
+        return cache[key][1]
+
     def input_proj_for(self, layer: int, precision: str):
         """Input-projection weight in the form bc_conv1d_fwd wants for ``precision`` (+ effective precision)."""
         w_in, bias, _ = self.packed(layer)
@@ -402,12 +414,17 @@ class ResLSTM(nn.Module):
     def forward_cl(self, x_cl):
         h = x_cl
         n = self.lstm.num_layers
+        precision = get_precision()
+        H = self.lstm.hidden_size
+        tc_batch = ops.lstm_tc_max_batch(H, precision) if LSTM_TENSOR_CORE[0] else 0
         for l in range(n):
-            _, _, w_rec = self.lstm.packed(l)
-            w_in, bias, prec = self.lstm.input_proj_for(l, get_precision())
-            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec,
-                             geometry=(1, h.shape[2], 4 * self.lstm.hidden_size))
-            h = ops.lstm_recurrent(pre, w_rec, x_cl if (self.skip and l == n - 1) else None)
+            w_in, bias, prec = self.lstm.input_proj_for(l, precision)
+            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
+            skip = x_cl if (self.skip and l == n - 1) else None
+            if tc_batch > 0:
+                h = ops.lstm_recurrent_tc(pre, self.lstm.recurrent_image_for(l, precision), skip, precision, tc_batch)
+            else:
+                h = ops.lstm_recurrent(pre, self.lstm.packed(l)[2], skip)
         return h
 
     @torch.no_grad()

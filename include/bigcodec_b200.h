@@ -148,6 +148,18 @@ int bc_lstm_pack_whh(const float* w_hh, float* packed, int H);
 int bc_lstm_recurrent_fwd(const float* pre, const float* w_hh_packed, const float* skip, float* y,
                           void* workspace, int B, int T, int H, bc_stream_t s);
 
+/* Tensor-core recurrence (BC_PREC_BF16 / BC_PREC_BF16X3): W_hh slices resident in shared memory, h
+ * exchanged between CTAs as bf16 (hi[, lo]) UMMA images through HBM/L2, per-batch-tile step counters
+ * instead of a grid barrier.  w_image = [4H/NS slices][split][H/16][2][NS][8] bf16 with slice row
+ * g*(NS/4)+u = W_hh[g*H + slice*(NS/4) + u], NS = bc_lstm_tc_slice_cols(precision).
+ * bc_lstm_tc_max_batch: largest B one launch accepts on the current device (0 = no tensor-core plan for
+ * this H; use bc_lstm_recurrent_fwd).  Workspace need not be zeroed. */
+int bc_lstm_tc_slice_cols(int precision);
+int bc_lstm_tc_max_batch(int H, int precision);
+size_t bc_lstm_tc_workspace_bytes(int B, int H, int precision);
+int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, const float* skip, float* y,
+                             void* workspace, int B, int T, int H, int precision, bc_stream_t s);
+
 /* ---- factorized VQ -------------------------------------------------------- */
 /* Replaces FactorizedVectorQuantize.forward / decode_latents in eval mode
  * (vq/factorized_vector_quantize.py:29-76,93-109): in_proj -> L2 normalise -> nearest
@@ -176,6 +188,9 @@ int bc_vq_dequant(const int32_t* idx, const float* cb, const float* w_out, const
 
 /* int32 [n_q][N] indices -> int16 [N][n_q], the on-disk layout of extract_indices.py:520-532. */
 int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_stream_t s);
+
+/* debug only: per-stage clock64 stamps of the persistent ResidualUnit kernel (CTA 0, first 64 tiles) */
+int bc_debug_set_ru_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

@@ -398,3 +398,29 @@ def test_fused_residual_unit_matches_oracle(precision, tol, C, dil, causal, T):
     assert got.shape == want.shape
     assert rel(got, want) <= tol
     assert rel(got, unfused) <= tol
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("H,layers,B,T", [(128, 2, 1, 1), (128, 1, 3, 40), (512, 2, 130, 25), (256, 2, 33, 64),
+                                          (512, 1, 257, 7)])
+def test_res_lstm_tensor_core_recurrence(precision, tol, H, layers, B, T):
+    """tcgen05 recurrence (W_hh resident in smem, h exchanged as bf16 hi/lo images, per-tile step counters):
+    several batch tiles, partial tiles, one-step sequences; and it must agree with the CUDA-core kernel."""
+    g = gen(H + layers + B + T)
+    m = M.ResLSTM(H, num_layers=layers)
+    sd = {"lstm." + k: v.data.clone() for k, v in m.lstm.named_parameters()}
+    x = torch.randn(B, H, T, generator=g)
+    want = oracle.res_lstm(sd, "", x, layers)
+    m = m.to(DEV)
+    M.set_precision(precision)
+    try:
+        assert ops.lstm_tc_max_batch(H, precision) >= 128
+        got = m(x.to(DEV))
+        M.LSTM_TENSOR_CORE[0] = False
+        ref = m(x.to(DEV))
+    finally:
+        M.LSTM_TENSOR_CORE[0] = True
+        M.set_precision("fp32")
+    assert got.shape == want.shape
+    assert rel(got, want) <= tol
+    assert rel(got, ref) <= tol
