@@ -52,6 +52,8 @@ struct TcParams {
   const float* sa2;
   const float* sib2;
   uint32_t region1_bytes;  // [A slab | B image], re-used for the bf16 intermediate of the fused tail
+  // persistent mode (single chunk, single n-tile): weights loaded once, CTA loops over (item, time-tile)
+  int persist, tiles_per_item, total_tiles;
 };
 
 constexpr int STAGE_BATCH = 4;  // slab items whose global loads are issued back to back per thread
@@ -74,11 +76,7 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
   const uint32_t mbar = smem_u32(bars), bbar = smem_u32(bars + 1), b2bar = smem_u32(bars + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
-  const int b = blockIdx.z;
   const int nt = blockIdx.y;
-  const int t0 = blockIdx.x * BM;
-  const int g0 = t0 * p.stride - p.pad_left;
-  const float* xb = p.x + (size_t)b * p.T_in * p.C_in;
   const bool snake = (p.flags & BC_CONV_SNAKE_IN) != 0;
 
   // ---- one-time setup: mbarriers, TMEM allocation, first weight image in flight ----
@@ -103,6 +101,14 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
   const int items = planes * p.slab_rows;  // 16-byte slab items per split
   const int pshift = 31 - __clz(planes);   // planes = 2*gpc is a power of two
   const int pl = tid & (planes - 1);        // ... and divides the block size: a thread always serves the same plane
+  // persistent mode: grid-stride over (item, time-tile); otherwise exactly one tile per CTA
+  const int tile_step = p.persist ? (int)gridDim.x : p.total_tiles;
+  for (int tile = p.persist ? (int)blockIdx.x : (int)(blockIdx.z * p.tiles_per_item + blockIdx.x); tile < p.total_tiles;
+       tile += tile_step) {
+  const int b = tile / p.tiles_per_item;
+  const int t0 = (tile - b * p.tiles_per_item) * BM;
+  const int g0 = t0 * p.stride - p.pad_left;
+  const float* xb = p.x + (size_t)b * p.T_in * p.C_in;
   for (int ch = 0; ch < p.nchunks; ++ch) {
     const int ci0 = ch * p.gpc * 16;
     // ---- stage A: x (fp32, HBM) -> snake -> bf16 hi[/lo] -> canonical K-major slab ----
@@ -144,31 +150,38 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
     // generic-proxy smem writes -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // ---- one thread issues every MMA of this chunk, then commits to the mbarrier ----
-    if (tid == 0) {
+    // ---- warp 0 runs the issue loop (warp-uniform), one elected lane issues each MMA and the commit ----
+    if (warp == 0) {
       mbar_wait(bbar, bphase);   // this chunk's weight image has landed (bulk copy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      for (int k = 0; k < p.K; ++k) {
-        const int sh = k * p.dil;
-        const uint32_t a_row = ((uint32_t)(sh % p.stride) * p.rpp + (uint32_t)(sh / p.stride)) * 16u;
-        for (int g = 0; g < p.gpc; ++g) {
-          const uint32_t a_off = (uint32_t)(2 * g) * plane_bytes + a_row;
-          const uint32_t b_off = (uint32_t)(k * p.gpc + g) * p.n_tile * 32u;
-#pragma unroll
-          for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
-            // term 0: a_hi*w_hi, 1: a_hi*w_lo, 2: a_lo*w_hi
-            const uint32_t aa = a_base + a_off + (term == 2 ? a_split_bytes : 0u);
-            const uint32_t bb = b_base + b_off + (term == 1 ? b_split_bytes : 0u);
-            const uint64_t ad = make_desc(aa, plane_bytes, 128u, p.variant);
-            const uint64_t bd = make_desc(bb, (uint32_t)p.n_tile * 16u, 128u, p.variant);
-            mma_bf16(tmem_base, ad, bd, p.idesc, (ch | k | g | term) ? 1u : 0u);
+      // descriptors are built from kernel parameters and loop counters only (uniform registers); one elected
+      // lane issues the whole chunk back to back
+      const uint32_t hi_d = desc_hi(128u);
+      const uint32_t smem0 = smem_u32(smem_raw);
+      const uint32_t a_lo0 = desc_lo(smem0, plane_bytes);
+      const uint32_t b_lo0 = desc_lo(smem0 + ((a_bytes + 127u) & ~127u), (uint32_t)p.n_tile * 16u);
+      const uint32_t a_g = (2u * plane_bytes) >> 4, b_g = ((uint32_t)p.n_tile * 32u) >> 4;
+      const uint32_t a_sp = a_split_bytes >> 4, b_sp = b_split_bytes >> 4;
+      if (elect_one()) {
+        uint32_t b_lo = b_lo0;
+        uint32_t acc = ch == 0 ? 0u : 1u;
+        for (int k = 0; k < p.K; ++k) {
+          const int sh = k * p.dil;
+          uint32_t a_lo = a_lo0 + (uint32_t)(sh % p.stride) * p.rpp + (uint32_t)(sh / p.stride);
+          for (int g = 0; g < p.gpc; ++g, a_lo += a_g, b_lo += b_g) {
+            mma_bf16_raw_rt(tmem_base, a_lo, b_lo, hi_d, hi_d, p.idesc, acc);
+            acc = 1u;
+            if (SPLIT == 2) {
+              mma_bf16_raw<true>(tmem_base, a_lo, b_lo + b_sp, hi_d, hi_d, p.idesc);   // a_hi * w_lo
+              mma_bf16_raw<true>(tmem_base, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);   // a_lo * w_hi
+            }
           }
         }
+        umma_commit(mbar);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+      __syncwarp();
     }
-    bphase ^= 1u;
+    if (!p.persist) bphase ^= 1u;   // persistent mode: the single weight image was loaded once (phase 0 stays complete)
     // everyone waits until the tensor core has consumed this chunk's smem
     mbar_wait(mbar, phase);
     phase ^= 1u;
@@ -217,20 +230,25 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     acc_col = (uint32_t)p.tmem_cols / 2;
-    if (tid == 0) {
+    if (warp == 0) {
       mbar_wait(b2bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_base = smem_u32(sA2), b_base = smem_u32(sB2);
-      for (int g = 0; g < p.n_tile / 16; ++g) {
-#pragma unroll
-        for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
-          const uint32_t aa = a_base + (uint32_t)(2 * g) * a2_plane + (term == 2 ? a2_split : 0u);
-          const uint32_t bb = b_base + (uint32_t)g * p.n_tile * 32u + (term == 1 ? b2_split_bytes : 0u);
-          mma_bf16(tmem_base + acc_col, make_desc(aa, a2_plane, 128u, p.variant),
-                   make_desc(bb, (uint32_t)p.n_tile * 16u, 128u, p.variant), p.idesc, (g | term) ? 1u : 0u);
+      const uint32_t hi_d = desc_hi(128u);
+      const uint32_t smem0 = smem_u32(smem_raw);
+      const uint32_t a_lo0 = desc_lo(smem0, a2_plane), b_lo0 = desc_lo(smem0 + p.region1_bytes, (uint32_t)p.n_tile * 16u);
+      const uint32_t a_g = (2u * a2_plane) >> 4, b_g = ((uint32_t)p.n_tile * 32u) >> 4;
+      if (elect_one()) {
+        uint32_t a_lo = a_lo0, b_lo = b_lo0;
+        for (int g = 0; g < p.n_tile / 16; ++g, a_lo += a_g, b_lo += b_g) {
+          mma_bf16_raw_rt(tmem_base + acc_col, a_lo, b_lo, hi_d, hi_d, p.idesc, g ? 1u : 0u);
+          if (SPLIT == 2) {
+            mma_bf16_raw<true>(tmem_base + acc_col, a_lo, b_lo + (b2_split_bytes >> 4), hi_d, hi_d, p.idesc);
+            mma_bf16_raw<true>(tmem_base + acc_col, a_lo + (a2_split >> 4), b_lo, hi_d, hi_d, p.idesc);
+          }
         }
+        umma_commit(mbar);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+      __syncwarp();
     }
   }
 
@@ -275,6 +293,10 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
       }
     }
   }
+  if (FUSE2) phase ^= 1u;   // the tail's commit completed one more mbarrier phase
+  // accumulator reads of this tile must be ordered before the next tile's MMAs (next __syncthreads)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }  // tile loop
   // ---- teardown ----
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -325,11 +347,19 @@ static int launch_tc(TcParams& p, int precision, cudaStream_t st) {
   const size_t b_bytes = (size_t)p.split * p.K * p.gpc * p.n_tile * 32;
   size_t region1 = ((a_bytes + 127) & ~size_t(127)) + ((b_bytes + 127) & ~size_t(127));
   size_t b2 = 0;
+  const size_t a2 = p.fuse2 ? (size_t)p.split * p.n_tile * BM * 2 : 0;   // bf16 intermediate tile(s)
   if (p.fuse2) {
-    const size_t a2 = (size_t)p.split * p.n_tile * BM * 2;   // bf16 intermediate tile(s)
     if (a2 > region1) region1 = (a2 + 127) & ~size_t(127);
     b2 = ((size_t)p.split * p.n_tile * p.n_tile * 2 + 127) & ~size_t(127);
   }
+  p.tiles_per_item = (p.T_out + BM - 1) / BM;
+  const long long total_tiles = (long long)p.tiles_per_item * p.B;
+  if (total_tiles > 2147483647ll) return fail(BC_EINVAL, "conv1d(tensor-core): too many tiles");
+  p.total_tiles = (int)total_tiles;
+  // persistent mode: one chunk, one n-tile, and (fused) the intermediate must fit inside the slab region alone
+  const char* pm = getenv("BC_TC_PERSIST");
+  p.persist = (p.nchunks == 1 && p.C_out == p.n_tile && (!p.fuse2 || a2 <= ((a_bytes + 127) & ~size_t(127))) &&
+               (pm && pm[0] == '1')) ? 1 : 0;   // opt-in: measured slower than the one-tile-per-CTA schedule
   p.region1_bytes = (uint32_t)region1;
   const size_t smem = region1 + b2 + 64;
   if (smem > 227 * 1024) return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): tile needs %zu B of shared memory", smem);
@@ -350,7 +380,17 @@ static int launch_tc(TcParams& p, int precision, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(conv1d_tc)");
     if (dev >= 0 && dev < 64) configured[dev][slot] = true;
   }
-  dim3 grid((p.T_out + BM - 1) / BM, p.C_out / p.n_tile, p.B);
+  dim3 grid(p.tiles_per_item, p.C_out / p.n_tile, p.B);
+  if (p.persist) {
+    int occ = 0, sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, smem);
+    if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    // TMEM: 512 columns per SM shared by the co-resident CTAs
+    if (occ * p.tmem_cols > 512) occ = 512 / p.tmem_cols;
+    const long long want = (long long)occ * sms;
+    grid = dim3((unsigned)(want < total_tiles ? want : total_tiles), 1, 1);
+  }
   kern<<<grid, TC_THREADS, smem, st>>>(p);
   BC_LAUNCH_CHECK("conv1d_tc_kernel");
   return BC_OK;

@@ -119,11 +119,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (warp-uniform loop, elected lane issues) =======================
+    {
       mbar_wait(bar_w, 0);
-      const uint32_t w_base = smem_u32(sW);
       const uint32_t a_plane = LM * 16u;
+      const uint32_t hi_d = desc_hi(128u);
+      const uint32_t w_lo0 = desc_lo(smem_u32(sW), (uint32_t)NS * 16u);
       uint32_t cc = 0;
       for (int t = 0; t < p.T; ++t) {
         mbar_wait(bar_acce, ((uint32_t)t & 1u) ^ 1u);   // gate warps have drained the accumulator of step t-1
@@ -132,21 +133,23 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
           mbar_wait(bar_full + 8u * slot, use & 1u);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA) + slot * slot_bytes;
+          uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes, a_plane);
+          uint32_t b_lo = w_lo0 + (((uint32_t)c * (KC / 16) * NS * 32u) >> 4);
+          const uint32_t a_g = (2u * a_plane) >> 4, b_g = ((uint32_t)NS * 32u) >> 4;
 #pragma unroll
-          for (int g = 0; g < KC / 16; ++g) {
-            const int kg = c * (KC / 16) + g;
-#pragma unroll
-            for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
-              const uint32_t aa = a_base + (uint32_t)(2 * g) * a_plane + (term == 2 ? chunk_split : 0u);
-              const uint32_t bb = w_base + (uint32_t)kg * NS * 32u + (term == 1 ? w_split : 0u);
-              mma_bf16(tmem_base, make_desc(aa, a_plane, 128u), make_desc(bb, (uint32_t)NS * 16u, 128u), p.idesc,
-                       (c | g | term) ? 1u : 0u);
+          for (int g = 0; g < KC / 16; ++g, a_lo += a_g, b_lo += b_g) {
+            if (g == 0 && c == 0) mma_bf16_lohi<false>(tmem_base, a_lo, b_lo, hi_d, hi_d, p.idesc);
+            else                  mma_bf16_lohi<true>(tmem_base, a_lo, b_lo, hi_d, hi_d, p.idesc);
+            if (SPLIT == 2) {
+              mma_bf16_lohi<true>(tmem_base, a_lo, b_lo + (w_split >> 4), hi_d, hi_d, p.idesc);
+              mma_bf16_lohi<true>(tmem_base, a_lo + (chunk_split >> 4), b_lo, hi_d, hi_d, p.idesc);
             }
           }
-          umma_commit(bar_empty + 8u * slot);
+          if (elect_one()) umma_commit(bar_empty + 8u * slot);
+          __syncwarp();
         }
-        umma_commit(bar_accf);
+        if (elect_one()) umma_commit(bar_accf);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

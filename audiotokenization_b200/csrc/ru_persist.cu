@@ -60,12 +60,12 @@ struct RuParams {
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
        B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
 
-template <int SPLIT>
+template <int SPLIT, int GROUPS>
 __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C;
-  const int planes = C / 8, groups = C / 16;
+  const int planes = C / 8;
   const uint32_t w7_split = (uint32_t)p.K * C * C * 2u;
   const uint32_t w1_split = (uint32_t)C * C * 2u;
   const uint32_t plane_bytes = (uint32_t)p.slab_rows * 16u;
@@ -184,12 +184,20 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
     }
   } else if (warp == MMA_WARP) {
-    // ======================= MMA issue (one thread) =======================
-    if (lane == 0) {
+    // ======================= MMA issue =======================
+    // All address arithmetic below is built from kernel parameters, blockIdx and loop counters only, so it
+    // stays in uniform registers; one elected lane issues a whole tile's MMAs back to back.
+    {
       int n_my = 0;
       for (int tile = first; tile < p.total_tiles; tile += step) ++n_my;
       mbar_wait(BAR(B_W_FULL), 0);
-      const uint32_t w7_base = smem_u32(sW7), w1_base = smem_u32(sW1);
+      const uint32_t smem0 = smem_u32(smem_raw);
+      const uint32_t uW7 = smem0, uW1 = uW7 + w7_split * SPLIT, uA = uW1 + w1_split * SPLIT, uA2 = uA + a_slot * p.nslot;
+      const uint32_t w7_lo0 = desc_lo(uW7, (uint32_t)C * 16u), w1_lo0 = desc_lo(uW1, (uint32_t)C * 16u);
+      const uint32_t hi_d = desc_hi(128u);
+      const uint32_t a_g = (2u * plane_bytes) >> 4, a_k = (uint32_t)p.dil, a_sp = a_split >> 4;
+      const uint32_t b_g = ((uint32_t)C * 32u) >> 4, b_sp = w7_split >> 4;
+      const uint32_t a2_g = (2u * a2_plane) >> 4;
       for (int it = 0; it <= n_my; ++it) {
         if (it < n_my) {  // K-tap conv of tile `it`
           const int slot = it % p.nslot, use = it / p.nslot, as = it & 1, ause = it >> 1;
@@ -197,22 +205,29 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
           TRACE(3);
-          const uint32_t a_base = smem_u32(sA + (size_t)slot * a_slot);
           const uint32_t d = tmem_base + (uint32_t)(as * p.n_pow2);
-          for (int k = 0; k < p.K; ++k) {
-            const uint32_t a_row = (uint32_t)(k * p.dil) * 16u;
-            for (int g = 0; g < groups; ++g) {
+          const uint32_t a_lo0 = desc_lo(uA + (uint32_t)slot * a_slot, plane_bytes);
+          if (elect_one()) {
 #pragma unroll
-              for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
-                const uint32_t aa = a_base + (uint32_t)(2 * g) * plane_bytes + a_row + (term == 2 ? a_split : 0u);
-                const uint32_t bb = w7_base + (uint32_t)(k * groups + g) * C * 32u + (term == 1 ? w7_split : 0u);
-                mma_bf16(d, make_desc(aa, plane_bytes, 128u), make_desc(bb, (uint32_t)C * 16u, 128u), p.idesc,
-                         (k | g | term) ? 1u : 0u);
+            for (int k = 0; k < 7; ++k) {
+              if (k < p.K) {
+#pragma unroll
+                for (int g = 0; g < GROUPS; ++g) {
+                  const uint32_t a_lo = a_lo0 + (uint32_t)k * a_k + (uint32_t)g * a_g;
+                  const uint32_t b_lo = w7_lo0 + (uint32_t)(k * GROUPS + g) * b_g;
+                  if (k == 0 && g == 0) mma_bf16_raw<false>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
+                  else                  mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
+                  if (SPLIT == 2) {
+                    mma_bf16_raw<true>(d, a_lo, b_lo + b_sp, hi_d, hi_d, p.idesc);          // a_hi * w_lo
+                    mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);          // a_lo * w_hi
+                  }
+                }
               }
             }
+            umma_commit(BAR(B_A_EMPTY + slot));
+            umma_commit(BAR(B_ACC1_FULL + as));
           }
-          umma_commit(BAR(B_A_EMPTY + slot));
-          umma_commit(BAR(B_ACC1_FULL + as));
+          __syncwarp();
           TRACE(4);
         }
         if (it >= 1) {  // 1x1 conv of tile `it - 1`
@@ -222,19 +237,23 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
           { const int it = j; TRACE(5); }
-          const uint32_t a_base = smem_u32(sA2 + (size_t)slot * a2_slot);
           const uint32_t d = tmem_base + (uint32_t)((2 + as) * p.n_pow2);
-          for (int g = 0; g < groups; ++g) {
+          const uint32_t a_lo0 = desc_lo(uA2 + (uint32_t)slot * a2_slot, a2_plane);
+          if (elect_one()) {
 #pragma unroll
-            for (int term = 0; term < (SPLIT == 2 ? 3 : 1); ++term) {
-              const uint32_t aa = a_base + (uint32_t)(2 * g) * a2_plane + (term == 2 ? a2_split : 0u);
-              const uint32_t bb = w1_base + (uint32_t)g * C * 32u + (term == 1 ? w1_split : 0u);
-              mma_bf16(d, make_desc(aa, a2_plane, 128u), make_desc(bb, (uint32_t)C * 16u, 128u), p.idesc,
-                       (g | term) ? 1u : 0u);
+            for (int g = 0; g < GROUPS; ++g) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)g * a2_g, b_lo = w1_lo0 + (uint32_t)g * b_g;
+              if (g == 0) mma_bf16_raw<false>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
+              else        mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
+              if (SPLIT == 2) {
+                mma_bf16_raw<true>(d, a_lo, b_lo + (w1_split >> 4), hi_d, hi_d, p.idesc);
+                mma_bf16_raw<true>(d, a_lo + (a2_split >> 4), b_lo, hi_d, hi_d, p.idesc);
+              }
             }
+            umma_commit(BAR(B_A2_EMPTY + slot));
+            umma_commit(BAR(B_ACC2_FULL + as));
           }
-          umma_commit(BAR(B_A2_EMPTY + slot));
-          umma_commit(BAR(B_ACC2_FULL + as));
+          __syncwarp();
           { const int it = j; TRACE(6); }
         }
       }
@@ -361,7 +380,7 @@ static long long* g_ru_trace = nullptr;
 
 // 0 = not applicable, else number of smem operand slots the persistent kernel would use
 int ru_persist_slots(int C, int K, int dilation, int precision) {
-  if (C != 16 && C != 32 && C != 64) return 0;   // power-of-two plane count; weights must stay resident
+  if ((C != 16 && C != 32 && C != 64) || K > 7) return 0;   // power-of-two plane count; weights must stay resident
   const char* off = getenv("BC_RU_PERSIST");
   if (off && off[0] == '0') return 0;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
@@ -374,7 +393,7 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
                         const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
                         int C, int K, int dilation, int pad_left, int precision, cudaStream_t st) {
   const int nslot = ru_persist_slots(C, K, dilation, precision);
-  if (nslot == 0) return fail(BC_EUNSUPPORTED, "resunit(persistent): C=%d K=%d dil=%d not supported", C, K, dilation);
+  if (nslot == 0 || K > 7) return fail(BC_EUNSUPPORTED, "resunit(persistent): C=%d K=%d dil=%d not supported", C, K, dilation);
   RuParams p;
   p.x = x; p.y = y; p.w7 = reinterpret_cast<const uint4*>(w7); p.w1 = reinterpret_cast<const uint4*>(w1);
   p.b7 = b7; p.b1 = b1; p.sa1 = sa1; p.sib1 = sib1; p.sa2 = sa2; p.sib2 = sib2;
@@ -391,15 +410,18 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
   const size_t smem = ru_smem_bytes(C, K, dilation, split, nslot);
   if ((size_t)p.slab_rows * 16 * 2 >= (1u << 18)) return fail(BC_EUNSUPPORTED, "resunit(persistent): descriptor offset overflow");
-  void (*kern)(const RuParams) = split == 2 ? ru_persist_kernel<2> : ru_persist_kernel<1>;
-  static bool configured[64][2] = {{false}};
+  void (*kern)(const RuParams) = nullptr;
+  const int gi = C == 16 ? 0 : (C == 32 ? 1 : 2);
+  if (split == 1) kern = gi == 0 ? ru_persist_kernel<1, 1> : (gi == 1 ? ru_persist_kernel<1, 2> : ru_persist_kernel<1, 4>);
+  else            kern = gi == 0 ? ru_persist_kernel<2, 1> : (gi == 1 ? ru_persist_kernel<2, 2> : ru_persist_kernel<2, 4>);
+  static bool configured[64][6] = {{false}};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (dev < 0 || dev >= 64 || !configured[dev][split - 1]) {
+  if (dev < 0 || dev >= 64 || !configured[dev][(split - 1) * 3 + gi]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(ru_persist)");
-    if (dev >= 0 && dev < 64) configured[dev][split - 1] = true;
+    if (dev >= 0 && dev < 64) configured[dev][(split - 1) * 3 + gi] = true;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   kern<<<grid, RU_THREADS, smem, st>>>(p);

@@ -32,5 +32,5 @@ for i in range(2, 26):
     print(f"{i:4d} " + " ".join(f"{int(t[i, j]) - base:9d}" if int(t[i, j]) else "        -" for j in range(12)))
 d = (t[20:60, 11] - t[19:59, 11]).float()
 print("steady-state cycles per tile (store_done deltas):", float(d.mean()))
-for a, b, label in [(0, 2, "LOAD total"), (0, 1, "LOAD until slot+data"), (1, 2, "LOAD convert"), (3, 4, "MMA7 issue"), (7, 8, "MID"), (9, 11, "STORE total"), (10, 11, "STORE after acc")]:
+for a, b, label in [(0, 2, "LOAD total"), (0, 1, "LOAD until slot+data"), (1, 2, "LOAD convert"), (3, 4, "MMA7 issue"), (7, 8, "MID"), (9, 11, "STORE total"), (10, 11, "STORE after acc"), (10, 12, "STORE tmem_load"), (12, 11, "STORE transpose+stores")]:
     print(f"  {label:24s} {float((t[10:60, b] - t[10:60, a]).float().mean()):8.0f} cycles")
