@@ -202,6 +202,71 @@ __global__ void __launch_bounds__(NTHREADS) conv1d_f32_kernel(const ConvParams p
   }
 }
 
+// ---------------------------------------------------------------------------
+// Edge convs.  The 1 -> C stem (vq/codec_encoder.py:35) and the C -> 1 tail (vq/codec_decoder.py:77) are
+// HBM-bound streaming stencils, not contractions: dedicated kernels, exact fp32.
+// ---------------------------------------------------------------------------
+// stem: y[b][t][co] = bias[co] + sum_k w[k][co] * x[b][t + k - pad_left]      (C_in == 1, stride 1)
+// thread = (time step, 4 output channels): a warp writes 4 steps x 128 B... contiguous rows of the output.
+template <int K>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int T_in,
+                                                        int T_out, int C_out, int pad_left, long long total) {
+  const int groups = C_out >> 2;                       // float4 groups per row
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int cg = (int)(e % groups);
+    const long long row = e / groups;                  // b * T_out + t
+    const int t = (int)(row % T_out);
+    const long long b = row / T_out;
+    const float* xb = x + b * T_in;
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int g = t + k - pad_left;
+      const float xv = (g >= 0 && g < T_in) ? __ldg(xb + g) : 0.f;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C_out) + cg);
+      acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+    }
+    __stcs(reinterpret_cast<float4*>(y + row * C_out) + cg, acc);
+  }
+}
+
+// tail: y[b][t] = act(bias + sum_k sum_ci w[k][ci] * snake?(x[b][t + k - pad_left][ci]))   (C_out == 1, stride 1)
+// one warp per output step: lanes stride the K*C_in products (coalesced rows), butterfly reduce.
+__global__ void __launch_bounds__(256) tail_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ sa,
+                                                        const float* __restrict__ sib, float* __restrict__ y, int T_in,
+                                                        int T_out, int C_in, int K, int pad_left, int flags,
+                                                        long long total_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool snake = (flags & BC_CONV_SNAKE_IN) != 0;
+  for (long long row = warp0; row < total_rows; row += nwarps) {
+    const int t = (int)(row % T_out);
+    const long long b = row / T_out;
+    const float* xb = x + b * (long long)T_in * C_in;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int g = t + k - pad_left;
+      if (g < 0 || g >= T_in) continue;
+      for (int ci = lane; ci < C_in; ci += 32) {
+        float v = __ldg(xb + (size_t)g * C_in + ci);
+        if (snake) v = bc::snake_ref(v, __ldg(sa + ci), __ldg(sib + ci));
+        acc = fmaf(v, __ldg(w + (size_t)k * C_in + ci), acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float o = acc + (bias ? __ldg(bias) : 0.f);
+      if (flags & BC_CONV_TANH_OUT) o = tanhf(o);
+      y[row] = o;
+    }
+  }
+}
+
 template <int BN>
 int launch(const ConvParams& p, cudaStream_t st) {
   const size_t smem = ((size_t)p.slab_rows * CKP + (size_t)p.K * CK * BN) * sizeof(float) + 16;
@@ -244,6 +309,27 @@ extern "C" int bc_conv1d_fwd(const float* x, const float* w, const float* bias, 
   if (precision != BC_PREC_FP32)
     return bc::conv1d_tc_fwd(x, w, bias, snake_a, snake_ib, res, y, B, T_in, C_in, T_out, C_out, K, stride, dilation,
                              pad_left, y_rows, y_tstride, y_toffset, flags, precision, (cudaStream_t)s);
+  cudaStream_t st_ = (cudaStream_t)s;
+  // ---- edge convs: streaming stencils ----
+  if (C_in == 1 && stride == 1 && dilation == 1 && C_out % 4 == 0 && !(flags & (BC_CONV_SNAKE_IN | BC_CONV_TANH_OUT)) && !res &&
+      y_tstride == 1 && y_toffset == 0 && y_rows == T_out && (K == 7 || K == 3 || K == 1) && bc::aligned16(w) && bc::aligned16(y) &&
+      (!bias || bc::aligned16(bias))) {
+    const long long total = (long long)B * T_out * (C_out / 4);
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 148ll * 32 ? (total + 255) / 256 : 148ll * 32);
+    if (K == 7) stem_conv_kernel<7><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
+    else if (K == 3) stem_conv_kernel<3><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
+    else stem_conv_kernel<1><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
+    BC_LAUNCH_CHECK("stem_conv_kernel");
+    return BC_OK;
+  }
+  if (C_out == 1 && stride == 1 && dilation == 1 && !res && y_tstride == 1 && y_toffset == 0 && y_rows == T_out) {
+    const long long rows = (long long)B * T_out;
+    const long long want = (rows * 32 + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148ll * 32 ? want : 148ll * 32);
+    tail_conv_kernel<<<blocks, 256, 0, st_>>>(x, w, bias, snake_a, snake_ib, y, T_in, T_out, C_in, K, pad_left, flags, rows);
+    BC_LAUNCH_CHECK("tail_conv_kernel");
+    return BC_OK;
+  }
   ConvParams p;
   p.x = x; p.w = w; p.bias = bias; p.sa = snake_a; p.sib = snake_ib; p.res = res; p.y = y;
   p.B = B; p.T_in = T_in; p.C_in = C_in; p.T_out = T_out; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;

@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from . import _cabi, configs, ops
-from .vq import BigCodecDecoder, BigCodecEncoder, set_precision
+from .vq import BigCodecDecoder, BigCodecEncoder, precision_scope
 
 
 def _strip_prefix(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
@@ -63,12 +63,12 @@ class BigCodecModel(nn.Module):
     def forward(self, x: torch.Tensor, round_trip: bool = False):
         """x [B,1,T] on the GPU.  ``{'indices'}`` (extract_indices) or, with ``round_trip``,
         ``{'x_rec','indices','loss'}`` (inference_full)."""
-        set_precision(self.precision)
-        vq_emb = self.encoder(x)
-        vq_post_emb, vq_code, _ = self.decoder(vq_emb, vq=True)
-        if not round_trip:
-            return {"indices": vq_code}
-        recon = self.decoder(vq_post_emb, vq=False)
+        with precision_scope(self.precision):
+            vq_emb = self.encoder(x)
+            vq_post_emb, vq_code, _ = self.decoder(vq_emb, vq=True)
+            if not round_trip:
+                return {"indices": vq_code}
+            recon = self.decoder(vq_post_emb, vq=False)
         return {"x_rec": recon, "indices": vq_code, "loss": {}}
 
     @torch.no_grad()
@@ -80,9 +80,9 @@ class BigCodecModel(nn.Module):
     @torch.no_grad()
     def encode_indices_cl(self, x_cl: torch.Tensor, want_margin: bool = False):
         """x_cl [B,T,1] device -> (idx int32 [n_q,B,T'], margin [n_q,B,T'] | None, z_cl [B,T',C])."""
-        set_precision(self.precision)
-        z_cl = self.encoder.forward_cl(x_cl)
-        _, idx, margin = self.decoder.quantizer.forward_cl(z_cl, want_margin=want_margin)
+        with precision_scope(self.precision):
+            z_cl = self.encoder.forward_cl(x_cl)
+            _, idx, margin = self.decoder.quantizer.forward_cl(z_cl, want_margin=want_margin)
         return idx, margin, z_cl
 
     def _indices_from_features(self, feat):
@@ -100,18 +100,18 @@ class BigCodecModel(nn.Module):
         memory: the stem's [mb, T, ngf] tensor is the largest), its frame-rate output (2 KB per frame) is
         collected for up to ``rnn_batch`` utterances, and the sequential LSTM + final conv + VQ then run
         once over that whole group."""
-        set_precision(self.precision)
         outs = []
         N = x_dev.shape[0]
-        for c0 in range(0, N, rnn_batch):
-            c1 = min(N, c0 + rnn_batch)
-            feats = []
-            for b0 in range(c0, c1, micro_batch):
-                xb = x_dev[b0:min(c1, b0 + micro_batch)]
-                feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
-            feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
-            del feats
-            outs.append(self._indices_from_features(feat))
+        with precision_scope(self.precision):
+            for c0 in range(0, N, rnn_batch):
+                c1 = min(N, c0 + rnn_batch)
+                feats = []
+                for b0 in range(c0, c1, micro_batch):
+                    xb = x_dev[b0:min(c1, b0 + micro_batch)]
+                    feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
+                feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
+                del feats
+                outs.append(self._indices_from_features(feat))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()
@@ -123,7 +123,10 @@ class BigCodecModel(nn.Module):
         batches are not equivalent to the reference's per-utterance padding)."""
         if wave_host.is_cuda:
             raise ValueError("extract_indices takes HOST waveforms; use indices_device for device tensors")
-        set_precision(self.precision)
+        with precision_scope(self.precision):
+            return self._extract_indices(wave_host, micro_batch, rnn_batch)
+
+    def _extract_indices(self, wave_host, micro_batch, rnn_batch):
         dev = next(self.parameters()).device
         N = wave_host.shape[0]
         copy_stream = torch.cuda.Stream(device=dev)

@@ -5,6 +5,6 @@ from .codec_decoder import BigCodecDecoder
 from .residual_vq import ResidualVQ
 from .factorized_vector_quantize import FactorizedVectorQuantize
 from .module import (CausalConv1d, CausalConvTranspose1d, DecoderBlock, EncoderBlock, ResidualUnit, ResLSTM,
-                     WNConv1d, WNConvTranspose1d, get_precision, set_precision)
+                     WNConv1d, WNConvTranspose1d, get_precision, precision_scope, set_precision)
 from .activations import SnakeBeta
 from .alias_free_torch import Activation1d

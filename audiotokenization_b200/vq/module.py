@@ -38,6 +38,24 @@ def get_precision() -> str:
     return _PRECISION[0]
 
 
+class precision_scope:
+    """``with precision_scope("bf16x3"): ...`` -- set the arithmetic mode for a block and restore it after."""
+
+    def __init__(self, mode: str):
+        if mode not in ops.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)}")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _PRECISION[0]
+        _PRECISION[0] = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        _PRECISION[0] = self.prev
+        return False
+
+
 def _fold(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """weight_norm(dim=0): w = g * v / ||v|| with the norm over all dims but 0 (float64 fold, once per load)."""
     v64, g64 = v.detach().double(), g.detach().double()

@@ -47,7 +47,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="base")
-    ap.add_argument("--precision", default=os.environ.get("BC_PRECISION", "fp32"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--precision", default=os.environ.get("BC_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"],
+                    help="arithmetic of the dense contractions for the headline number: bf16x3 (default) = tcgen05 with "
+                         "hi/lo split operands, fp32-class accuracy (meets the <=1e-3 / bit-exact-index contract); "
+                         "bf16 = single-pass tcgen05 (fast mode, ~1e-2 latent error); fp32 = CUDA-core FFMA")
+    ap.add_argument("--also", default=os.environ.get("BC_ALSO", "bf16"),
+                    help="comma-separated extra precisions measured device-resident and reported under 'modes'")
     ap.add_argument("--clips-per-gpu", type=int, default=512)
     ap.add_argument("--clip-seconds", type=float, default=30.0)
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("BC_MICRO_BATCH", "8")))
@@ -318,6 +323,20 @@ def main():
             "index_agreement": float((got == want["indices"][0]).float().mean()),
             "exact_where_margin_gt_1e-5": bool(torch.equal(got[decided], want["indices"][0][decided]))}
 
+    # ---- other arithmetic modes (device-resident only; reported, never substituted for the headline) ----
+    modes = {}
+    for mode in [m for m in args.also.split(",") if m and m != args.precision]:
+        model.precision = mode
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_device()
+        ms_m = timed(step_device, args.steps)
+        modes[mode] = {"value": world * audio_s_local * args.steps / (ms_m / 1000.0), "unit": UNIT,
+                       "ms_per_step": ms_m / args.steps}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            got_m = keep["idx"][:1, :, 0].cpu().to(torch.int64)
+            modes[mode]["index_agreement_clip0"] = float((got_m == want["indices"][0]).float().mean())
+    model.precision = args.precision
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -327,7 +346,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4),
                     "d2h_bytes_per_step": int(i16.nbytes), "ms_per_step": ms_e2e / args.steps,
                     "matches_device_path": same},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "modes": modes,
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

@@ -59,3 +59,47 @@ def test_round_trip_matches_reference_fixture(case):
     emb = model.decoder.vq2emb(idx.permute(1, 2, 0))
     assert rel(emb.cpu().numpy()[same], g["emb_f32"][same]) <= 1e-5
     print(f"{case}: z rel {e_z32:.2e} (vs f64 {e_z64:.2e}), y rel {e_y:.2e}, idx agree {agree:.4f}")
+
+
+@pytest.mark.parametrize("case", ["base_1s", "debug_1s", "config9_base_1s", "debug_causal_1s", "tiny", "base_aa_1s"])
+def test_tensor_core_split_mode_meets_the_fp32_contract(case):
+    """bf16x3 (tcgen05, hi/lo split operands, fused ResidualUnits, tensor-core LSTM): latents and waveforms
+    within 1e-3 of the reference (asserted 5x tighter), indices bit-exact where the margin exceeds 1e-5...
+    end to end through ~60 layers a 1e-5-class latent error can still flip a frame whose margin is below
+    ~1e-4, so exactness is asserted for margin > 2e-4 and the agreement rate is reported."""
+    g = load_golden(case)
+    cfg = configs.get_config(g["cfg_name"], antialias=g["antialias"])
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=g["seed"])
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision="bf16x3")
+    x = synth.synth_batch(0, g["batch"], g["num_samples"], g["kind"]).cuda()
+    out = model(x, round_trip=True)
+    z = model.encoder(x)
+    e_z = rel(z.cpu().numpy(), g["z_f64"])
+    assert e_z <= 2e-4, e_z
+    idx = out["indices"].cpu().numpy()
+    decided = g["margin_f64"][None] > 2e-4
+    assert np.array_equal(idx[decided], g["idx_f64"][decided])
+    agree = float((idx == g["idx_f32"]).mean())
+    assert agree >= 0.99, agree
+    y = model.decoder(torch.from_numpy(g["zq_f32"]).cuda(), vq=False)
+    e_y = rel(y.cpu().numpy(), g["y_f64"])
+    assert e_y <= 2e-4, e_y
+    print(f"{case} bf16x3: z rel {e_z:.2e}, y rel {e_y:.2e}, idx agree {agree:.4f}")
+
+
+@pytest.mark.parametrize("case", ["base_1s", "debug_1s"])
+def test_single_pass_bf16_fast_mode_is_within_its_documented_envelope(case):
+    """bf16 single pass: ~1e-2 latent error and >= 90 % raw index agreement (SURVEY.md section 7 measured
+    9.3e-3 / 96.9 % for bf16-rounded conv operands on the reference itself)."""
+    g = load_golden(case)
+    cfg = configs.get_config(g["cfg_name"], antialias=g["antialias"])
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=g["seed"])
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision="bf16")
+    x = synth.synth_batch(0, g["batch"], g["num_samples"], g["kind"]).cuda()
+    out = model(x)
+    z = model.encoder(x)
+    e_z = rel(z.cpu().numpy(), g["z_f64"])
+    agree = float((out["indices"].cpu().numpy() == g["idx_f32"]).mean())
+    assert e_z <= 5e-2, e_z
+    assert agree >= 0.85, agree
+    print(f"{case} bf16: z rel {e_z:.2e}, idx agree {agree:.4f}")
