@@ -470,5 +470,17 @@ extern "C" int bc_resunit_plan(int C, int K, int dilation, int precision, int* n
   *persistent = 0;
   int rc = bc::tc_plan(C, C, K, 1, dilation, precision, n_tile, gpc, nchunks);
   if (rc != BC_OK || *n_tile != C) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: C=%d K=%d has no fused tensor-core plan", C, K);
+  // the per-tile fused kernel only pays off while two CTAs still fit on an SM (measured: C=128 in the
+  // split-precision mode needs 133 KB and is faster as two separate launches)
+  {
+    const size_t split = precision == BC_PREC_BF16X3 ? 2 : 1;
+    const size_t slab_rows = 127 + (size_t)(K - 1) * dilation + 1;
+    const size_t a_bytes = split * 2 * (*gpc) * slab_rows * 16, b_bytes = split * K * (*gpc) * C * 32;
+    size_t region1 = ((a_bytes + 127) & ~size_t(127)) + ((b_bytes + 127) & ~size_t(127));
+    const size_t a2 = split * C * 128 * 2;
+    if (a2 > region1) region1 = a2;
+    const size_t smem = region1 + split * C * C * 2 + 64;
+    if (smem > 110 * 1024) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: fused tile needs %zu B of shared memory; chain two convs", smem);
+  }
   return BC_OK;
 }

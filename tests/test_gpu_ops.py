@@ -388,7 +388,8 @@ def test_fused_residual_unit_matches_oracle(precision, tol, C, dil, causal, T):
     ru = ru.to(DEV)
     M.set_precision(precision)
     try:
-        assert ru._fused_plan(precision) is not None
+        if not (precision == "bf16x3" and C > 64):   # C=128 split mode: too much smem for 2 CTAs/SM -> two launches
+            assert ru._fused_plan(precision) is not None
         got = ru(x.to(DEV))
         M.FUSE_RESUNIT[0] = False
         unfused = ru(x.to(DEV))
