@@ -233,38 +233,45 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 }
 
 // tail: y[b][t] = act(bias + sum_k sum_ci w[k][ci] * snake?(x[b][t + k - pad_left][ci]))   (C_out == 1, stride 1)
-// one warp per output step: lanes stride the K*C_in products (coalesced rows), butterfly reduce.
-__global__ void __launch_bounds__(256) tail_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, const float* __restrict__ sa,
-                                                        const float* __restrict__ sib, float* __restrict__ y, int T_in,
-                                                        int T_out, int C_in, int K, int pad_left, int flags,
-                                                        long long total_rows) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+// CTA = 256 consecutive output steps of one item.  The activated input rows are staged ONCE in shared
+// memory (row stride C_in + 1: conflict-free column walks), then thread t walks its K x C_in window.
+constexpr int TAIL_TT = 256;
+__global__ void __launch_bounds__(TAIL_TT) tail_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, const float* __restrict__ sa,
+                                                            const float* __restrict__ sib, float* __restrict__ y, int T_in,
+                                                            int T_out, int C_in, int K, int pad_left, int flags) {
+  extern __shared__ float tail_smem[];
+  const int ld = C_in + 1;
+  const int rows = TAIL_TT + K - 1;
+  float* sx = tail_smem;               // [rows][ld]
+  float* sw = sx + (size_t)rows * ld;  // [K][C_in]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TAIL_TT;
+  const float* xb = x + (size_t)b * T_in * C_in;
   const bool snake = (flags & BC_CONV_SNAKE_IN) != 0;
-  for (long long row = warp0; row < total_rows; row += nwarps) {
-    const int t = (int)(row % T_out);
-    const long long b = row / T_out;
-    const float* xb = x + b * (long long)T_in * C_in;
-    float acc = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const int g = t + k - pad_left;
-      if (g < 0 || g >= T_in) continue;
-      for (int ci = lane; ci < C_in; ci += 32) {
-        float v = __ldg(xb + (size_t)g * C_in + ci);
-        if (snake) v = bc::snake_ref(v, __ldg(sa + ci), __ldg(sib + ci));
-        acc = fmaf(v, __ldg(w + (size_t)k * C_in + ci), acc);
-      }
+  for (int i = threadIdx.x; i < K * C_in; i += TAIL_TT) sw[i] = __ldg(w + i);
+  for (int i = threadIdx.x; i < rows * C_in; i += TAIL_TT) {
+    const int r = i / C_in, c = i - r * C_in;
+    const int g = t0 + r - pad_left;
+    float v = 0.f;
+    if (g >= 0 && g < T_in) {
+      v = __ldg(xb + (size_t)g * C_in + c);
+      if (snake) v = bc::snake_ref(v, __ldg(sa + c), __ldg(sib + c));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      float o = acc + (bias ? __ldg(bias) : 0.f);
-      if (flags & BC_CONV_TANH_OUT) o = tanhf(o);
-      y[row] = o;
-    }
+    sx[r * ld + c] = v;
   }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T_out) return;
+  float acc = bias ? __ldg(bias) : 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* row = sx + (size_t)(threadIdx.x + k) * ld;
+    const float* wk = sw + k * C_in;
+#pragma unroll 8
+    for (int c = 0; c < C_in; ++c) acc = fmaf(row[c], wk[c], acc);
+  }
+  if (flags & BC_CONV_TANH_OUT) acc = tanhf(acc);
+  y[(size_t)b * T_out + t] = acc;
 }
 
 template <int BN>
@@ -322,11 +329,15 @@ extern "C" int bc_conv1d_fwd(const float* x, const float* w, const float* bias, 
     BC_LAUNCH_CHECK("stem_conv_kernel");
     return BC_OK;
   }
-  if (C_out == 1 && stride == 1 && dilation == 1 && !res && y_tstride == 1 && y_toffset == 0 && y_rows == T_out) {
-    const long long rows = (long long)B * T_out;
-    const long long want = (rows * 32 + 255) / 256;
-    const unsigned blocks = (unsigned)(want < 148ll * 32 ? want : 148ll * 32);
-    tail_conv_kernel<<<blocks, 256, 0, st_>>>(x, w, bias, snake_a, snake_ib, y, T_in, T_out, C_in, K, pad_left, flags, rows);
+  if (C_out == 1 && stride == 1 && dilation == 1 && !res && y_tstride == 1 && y_toffset == 0 && y_rows == T_out &&
+      (size_t)((TAIL_TT + K - 1) * (C_in + 1) + K * C_in) * sizeof(float) <= 160 * 1024) {
+    const size_t smem = (size_t)((TAIL_TT + K - 1) * (C_in + 1) + K * C_in) * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(tail_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(tail_conv)");
+    }
+    dim3 grid((T_out + TAIL_TT - 1) / TAIL_TT, B);
+    tail_conv_kernel<<<grid, TAIL_TT, smem, st_>>>(x, w, bias, snake_a, snake_ib, y, T_in, T_out, C_in, K, pad_left, flags);
     BC_LAUNCH_CHECK("tail_conv_kernel");
     return BC_OK;
   }
