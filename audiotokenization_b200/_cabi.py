@@ -33,6 +33,9 @@ _SIGNATURES = {
     "bc_tc_plan": (c_int, [c_int] * 6 + [POINTER(c_int)] * 3),
     "bc_resunit_plan": (c_int, [c_int] * 4 + [POINTER(c_int)] * 4),
     "bc_resunit_fwd": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_void_p]),
+    "bc_stream_plan": (c_int, [c_int] * 7 + [POINTER(c_int)]),
+    "bc_conv1d_stream_fwd": (c_int, [c_void_p] * 7 + [c_int] * 11 + [c_void_p]),
+    "bc_resunit_stream_fwd": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_void_p]),
     "bc_convtr1d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bc_lstm_workspace_bytes": (c_size_t, [c_int, c_int]),
     "bc_lstm_packed_whh_floats": (c_size_t, [c_int]),
@@ -45,6 +48,7 @@ _SIGNATURES = {
     "bc_vq_encode": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "bc_debug_set_ru_trace": (c_int, [c_void_p]),
+    "bc_debug_set_stream_trace": (c_int, [c_void_p]),
     "bc_indices_to_int16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 

@@ -223,6 +223,76 @@ def pack_tc_weight(w_kio: torch.Tensor, plan, precision: str) -> torch.Tensor:
     return torch.stack(parts, dim=2).contiguous()
 
 
+def stream_plan(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision: str, fused: bool = False):
+    """n_tile of the streamed-weight persistent kernel (bc_stream_plan), or None when the geometry has no plan."""
+    if precision == "fp32":
+        return None
+    key = ("stream", c_in, c_out, k, stride, dilation, precision, bool(fused))
+    if key not in _TC_PLANS:
+        import ctypes
+        nt = ctypes.c_int()
+        rc = load_library().bc_stream_plan(c_in, c_out, k, stride, dilation, PRECISIONS[precision], int(bool(fused)),
+                                           ctypes.byref(nt))
+        _TC_PLANS[key] = nt.value if rc == 0 else None
+    return _TC_PLANS[key]
+
+
+def pack_stream_weight(w_kio: torch.Tensor, n_tile: int, precision: str) -> torch.Tensor:
+    """fp32 [K, C_in, C_out] -> bf16 image [C_out/n_tile][C_in/16][K][split][2][n_tile][8] of the streamed-weight
+    kernel: one (16-channel group, tap) block after the other in the order the kernel consumes them."""
+    K, c_in, c_out = w_kio.shape
+    w = w_kio.float()
+    hi = w.to(torch.bfloat16)
+
+    def image(t):   # (k, g, h, e, nt, n) -> (nt, g, k, h, n, e)
+        return t.reshape(K, c_in // 16, 2, 8, c_out // n_tile, n_tile).permute(4, 1, 0, 2, 5, 3)
+
+    parts = [image(hi)]
+    if precision == "bf16x3":
+        parts.append(image((w - hi.float()).to(torch.bfloat16)))
+    return torch.stack(parts, dim=3).contiguous()
+
+
+def conv1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], *, k: int, c_out: int,
+                  stride: int = 1, dilation: int = 1, pad_left: int = 0, t_out: int,
+                  snake_a: Optional[torch.Tensor] = None, snake_ib: Optional[torch.Tensor] = None,
+                  res: Optional[torch.Tensor] = None, tanh: bool = False, precision: str) -> torch.Tensor:
+    """Dense conv on the persistent streamed-weight kernel (``w_img`` from pack_stream_weight)."""
+    x = _cl(x)
+    B, T_in, C_in = x.shape
+    if t_out <= 0:
+        raise ValueError(f"conv1d: input of {T_in} steps is too short for this layer (T_out={t_out})")
+    y = torch.empty((B, t_out, c_out), device=x.device, dtype=torch.float32)
+    flags = (BC_CONV_SNAKE_IN if snake_a is not None else 0) | (BC_CONV_TANH_OUT if tanh else 0)
+    if res is not None:
+        res = _cl(res, "res")
+        if tuple(res.shape) != (B, t_out, c_out):
+            raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, c_out)}")
+    with _Timed(("conv1d", C_in, c_out, k, stride, dilation, t_out, B, precision), 2.0 * B * t_out * c_out * C_in * k, x.device):
+        check(load_library().bc_conv1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res),
+                                                  ptr(y), B, T_in, C_in, t_out, c_out, k, stride, dilation, pad_left,
+                                                  flags, PRECISIONS[precision], stream_ptr(x.device)),
+              "bc_conv1d_stream_fwd")
+    _count()
+    return y
+
+
+def resunit_stream(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, b1, sa2, sib2, *, k: int,
+                   dilation: int, pad_left: int, precision: str) -> torch.Tensor:
+    """Fused ResidualUnit on the persistent streamed-weight kernel (wide layers)."""
+    x = _cl(x)
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    flops = 2.0 * B * T * C * C * (k + 1)
+    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device):
+        check(load_library().bc_resunit_stream_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1),
+                                                   ptr(sa2), ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left,
+                                                   PRECISIONS[precision], stream_ptr(x.device)),
+              "bc_resunit_stream_fwd")
+    _count()
+    return y
+
+
 LSTM_MAX_BATCH = 256
 
 

@@ -24,6 +24,18 @@ from .alias_free_torch import Activation1d
 _PRECISION = ["fp32"]
 LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
+STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
+STREAM_MIN_CIN = [64]   # ... when the layer has at least this many input channels (narrow layers: weights stay resident)
+STREAM_RU_MIN_C = [128]
+
+
+def _stream_tile(c_in, c_out, k, stride, dilation, precision, fused=False):
+    """n_tile of the streamed-weight kernel when policy and geometry select it, else None."""
+    if precision == "fp32" or not STREAM[0]:
+        return None
+    if c_in < (STREAM_RU_MIN_C[0] if fused else STREAM_MIN_CIN[0]):
+        return None
+    return ops.stream_plan(c_in, c_out, k, stride, dilation, precision, fused)
 
 
 def set_precision(mode: str) -> None:
@@ -125,11 +137,26 @@ class _Conv1dWN(_WNParams):
             cache.update(key=key, w=ops.pack_tc_weight(w, plan, precision))
         return cache["w"], b, precision
 
+    def stream_image(self, precision: str, n_tile: int):
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        key = (precision, n_tile, self._key())
+        if cache.get("key") != key:
+            cache.clear()
+            cache.update(key=key, w=ops.pack_stream_weight(self.packed()[0], n_tile, precision))
+        return cache["w"]
+
     def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None, res=None, tanh=False):
-        w, b, prec = self.packed_for(get_precision())
         a = ib = None
         if act is not None:
             a, ib = act.device_params()
+        precision = get_precision()
+        nt = _stream_tile(self.in_channels, self.out_channels, self.kernel_size, self.stride, self.dilation, precision)
+        if nt is not None:
+            return ops.conv1d_stream(x_cl, self.stream_image(precision, nt), self.packed()[1], k=self.kernel_size,
+                                     c_out=self.out_channels, stride=self.stride, dilation=self.dilation,
+                                     pad_left=self.left_pad, t_out=self.out_length(x_cl.shape[1]), snake_a=a,
+                                     snake_ib=ib, res=res, tanh=tanh, precision=precision)
+        w, b, prec = self.packed_for(precision)
         return ops.conv1d(x_cl, w, b, stride=self.stride, dilation=self.dilation, pad_left=self.left_pad,
                           t_out=self.out_length(x_cl.shape[1]), snake_a=a, snake_ib=ib, res=res, tanh=tanh,
                           precision=prec)
@@ -281,8 +308,27 @@ class ResidualUnit(nn.Module):
             return None
         return conv7, conv1, plan[0], (C, C // 16, 1)
 
+    def _stream_forward(self, x_cl, prec):
+        """Whole unit on the streamed-weight kernel (wide layers), or None."""
+        if not FUSE_RESUNIT[0] or self.block[0].antialias:
+            return None
+        conv7 = self.block[1].conv if isinstance(self.block[1], CausalConv1d) else self.block[1]
+        conv1 = self.block[3]
+        C = conv7.in_channels
+        nt = _stream_tile(C, C, conv7.kernel_size, 1, conv7.dilation, prec, fused=True)
+        if nt is None:
+            return None
+        sa1, sib1 = self.block[0].act.device_params()
+        sa2, sib2 = self.block[2].act.device_params()
+        return ops.resunit_stream(x_cl, conv7.stream_image(prec, nt), conv7.packed()[1], sa1, sib1,
+                                  conv1.stream_image(prec, nt), conv1.packed()[1], sa2, sib2, k=conv7.kernel_size,
+                                  dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec)
+
     def forward_cl(self, x_cl):
         prec = get_precision()
+        y = self._stream_forward(x_cl, prec)
+        if y is not None:
+            return y
         fused = self._fused_plan(prec)
         if fused is None:
             h = _act_conv(self.block[0], self.block[1], x_cl)
@@ -419,6 +465,16 @@ class _LSTMParams(nn.Module):
         return cache[key], bias, precision
 
 
+    def input_proj_stream(self, layer: int, precision: str, n_tile: int):
+        """Input-projection weight as the streamed-weight image."""
+        w_in, _, _ = self.packed(layer)
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        key = (layer, precision, n_tile, w_in.data_ptr())
+        if key not in cache:
+            cache[key] = ops.pack_stream_weight(w_in, n_tile, precision)
+        return cache[key]
+
+
 class ResLSTM(nn.Module):
     """y = LSTM(x^T) + x^T (vq/module.py:143-167); uni-directional only on the hot path."""
 
@@ -436,8 +492,13 @@ class ResLSTM(nn.Module):
         H = self.lstm.hidden_size
         tc_batch = ops.lstm_tc_max_batch(H, precision) if LSTM_TENSOR_CORE[0] else 0
         for l in range(n):
-            w_in, bias, prec = self.lstm.input_proj_for(l, precision)
-            pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
+            nt = _stream_tile(h.shape[2], 4 * H, 1, 1, 1, precision)
+            if nt is not None:
+                pre = ops.conv1d_stream(h, self.lstm.input_proj_stream(l, precision, nt), self.lstm.packed(l)[1], k=1,
+                                        c_out=4 * H, t_out=h.shape[1], precision=precision)
+            else:
+                w_in, bias, prec = self.lstm.input_proj_for(l, precision)
+                pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
             skip = x_cl if (self.skip and l == n - 1) else None
             if tc_batch > 0:
                 h = ops.lstm_recurrent_tc(pre, self.lstm.recurrent_image_for(l, precision), skip, precision, tc_batch)

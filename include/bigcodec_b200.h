@@ -121,6 +121,24 @@ int bc_resunit_fwd(const float* x, const float* w7, const float* b7, const float
                    const float* w1, const float* b1, const float* snake2_a, const float* snake2_ib, float* y,
                    int B, int T, int C, int K, int dilation, int pad_left, int precision, bc_stream_t s);
 
+/* Streamed-weight persistent kernels for the wide layers (tensor-core modes): one CTA per SM walks the
+ * (n-tile, item, 128-step) tiles while the weights flow from L2 through a shared-memory ring in
+ * (16-channel group, tap) units; activation staging, MMA issue, the ResidualUnit's middle activation and
+ * the output stores run on separate warps (csrc/conv_stream.cu).  Same arithmetic and arguments as
+ * bc_conv1d_fwd (y_rows = T_out, y_tstride = 1, y_toffset = 0) / bc_resunit_fwd; the weight image is
+ *   [C_out/n_tile][C_in/16][K][split][2][n_tile][8] bf16,  input channel = g*16 + h*8 + e,
+ * n_tile from bc_stream_plan (BC_EUNSUPPORTED: no plan, use bc_conv1d_fwd / bc_resunit_fwd).
+ * `fused` = 1 asks for the ResidualUnit plan (W7 image as above, W1 image with K = 1). */
+int bc_stream_plan(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused, int* n_tile);
+int bc_conv1d_stream_fwd(const float* x, const void* w_image, const float* bias, const float* snake_a,
+                         const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                         int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
+                         bc_stream_t s);
+int bc_resunit_stream_fwd(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
+                          const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
+                          const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
+                          int precision, bc_stream_t s);
+
 /* Transposed conv as `stride` output phases of 2-tap convs:
  * w_phases[phase][2][C_in][C_out] (host-packed from the folded [C_in,C_out,2*stride]
  * weight: tap0 = W[:,:,j0+stride], tap1 = W[:,:,j0], j0 = (phase+padding) % stride).
@@ -191,6 +209,8 @@ int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_str
 
 /* debug only: per-stage clock64 stamps of the persistent ResidualUnit kernel (CTA 0, first 64 tiles) */
 int bc_debug_set_ru_trace(void* device_buffer);
+/* same for the streamed-weight kernel (events: producer, MMA, MID, store stamps and MMA-warp wait totals) */
+int bc_debug_set_stream_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

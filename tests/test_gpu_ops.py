@@ -425,3 +425,96 @@ def test_res_lstm_tensor_core_recurrence(precision, tol, H, layers, B, T):
     assert got.shape == want.shape
     assert rel(got, want) <= tol
     assert rel(got, ref) <= tol
+
+
+# ---------------------------------------------------------------------------------------------
+# persistent streamed-weight kernels (csrc/conv_stream.cu)
+# ---------------------------------------------------------------------------------------------
+STREAM_CONV_CASES = [
+    # cin, cout, k, stride, dil, pad, B, T
+    (128, 128, 7, 1, 9, 27, 2, 260),
+    (256, 256, 7, 1, 3, 9, 1, 140),
+    (64, 128, 8, 4, 1, 2, 2, 1000),
+    (128, 256, 10, 5, 1, 3, 3, 999),
+    (256, 512, 10, 5, 1, 3, 2, 400),
+    (512, 512, 3, 1, 1, 1, 2, 80),
+    (512, 2048, 1, 1, 1, 0, 1, 100),
+    (64, 64, 1, 1, 1, 0, 2, 513),
+    (128, 128, 7, 1, 1, 3, 5, 5000),      # more tiles than SMs: every CTA walks several tiles
+    (256, 256, 1, 1, 1, 0, 3, 9000),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,dil,pad,B,T", STREAM_CONV_CASES)
+@pytest.mark.parametrize("precision,fused_act", [("bf16x3", True), ("bf16", True), ("bf16x3", False)])
+def test_stream_conv_matches_oracle_and_tile_kernel(cin, cout, k, stride, dil, pad, B, T, precision, fused_act):
+    g = gen(cin * 5 + cout + k + T)
+    conv = M.WNConv1d(cin, cout, kernel_size=k, stride=stride, dilation=dil, padding=pad)
+    conv.weight_g.data *= torch.exp(torch.randn(cout, 1, 1, generator=g) * 0.2)
+    conv.bias.data = torch.randn(cout, generator=g) * 0.2
+    x = torch.randn(B, cin, T, generator=g)
+    r = torch.randn(B, cout, conv.out_length(T), generator=g)
+    w = oracle.fold_weight_norm(conv.weight_g.double(), conv.weight_v.double())
+    xin = x.double()
+    act = None
+    if fused_act:
+        act = SnakeBeta(cin, alpha_logscale=True)
+        act.alpha.data = torch.randn(cin, generator=g) * 0.3
+        act.beta.data = torch.randn(cin, generator=g) * 0.3
+        xin = oracle.snake_beta(x, act.alpha.data, act.beta.data).double()
+        act = act.to(DEV)
+    exact = F.conv1d(xin, w, conv.bias.double(), stride=stride, dilation=dil, padding=pad) + r.double()
+    conv = conv.to(DEV)
+    xc, rc = ops.to_channels_last(x.to(DEV)), ops.to_channels_last(r.to(DEV))
+    M.set_precision(precision)
+    try:
+        assert M._stream_tile(cin, cout, k, stride, dil, precision) is not None
+        got = conv.forward_cl(xc, act=act, res=rc).permute(0, 2, 1)
+        M.STREAM[0] = False
+        tile = conv.forward_cl(xc, act=act, res=rc).permute(0, 2, 1)
+    finally:
+        M.STREAM[0] = True
+        M.set_precision("fp32")
+    assert got.shape == exact.shape
+    if precision == "bf16x3":
+        assert rel(got, exact) <= 3e-5
+    else:
+        assert rel(got, exact) <= 1e-2
+    assert rel(got, tile) <= (2e-6 if precision == "bf16" else 3e-5)   # same operands, other summation order
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 5e-5), ("bf16", 1.5e-2)])
+@pytest.mark.parametrize("C,dil,causal,B,T", [(128, 1, False, 2, 1000), (128, 9, False, 5, 5000), (256, 3, False, 2, 777),
+                                              (256, 9, False, 3, 7000), (64, 9, False, 2, 300), (128, 3, True, 1, 333),
+                                              (128, 9, False, 1, 30)])
+def test_stream_residual_unit_matches_oracle(precision, tol, C, dil, causal, B, T):
+    g = gen(C + dil + T)
+    ru = M.ResidualUnit(C, dilation=dil, causal=causal)
+    sd = {}
+    for name, prm in ru.named_parameters():
+        if name.endswith(("alpha", "beta")):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.3
+        elif name.endswith("bias"):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.2
+        elif name.endswith("weight_g"):
+            prm.data = prm.data * torch.exp(torch.randn(prm.shape, generator=g) * 0.2)
+    for name, prm in ru.named_parameters():
+        sd[name] = prm.data.clone().double()
+    x = torch.randn(B, C, T, generator=g)
+    want = oracle.residual_unit(sd, "", x.double(), dil, causal, False)
+    ru = ru.to(DEV)
+    M.set_precision(precision)
+    old_min = M.STREAM_RU_MIN_C[0]
+    try:
+        M.STREAM_RU_MIN_C[0] = 64
+        assert M._stream_tile(C, C, 7, 1, dil, precision, fused=True) is not None
+        got = ru(x.to(DEV))
+        M.STREAM[0] = False
+        other = ru(x.to(DEV))
+    finally:
+        M.STREAM[0] = True
+        M.STREAM_RU_MIN_C[0] = old_min
+        M.set_precision("fp32")
+    assert got.shape == want.shape
+    assert rel(got, want) <= tol
+    assert rel(got, other) <= tol
