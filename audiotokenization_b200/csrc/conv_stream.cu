@@ -12,7 +12,7 @@
 //   warp  21     MMA      K-tap conv: groups x taps [x3] tcgen05.mma into acc1 (TMEM)            (acc1_full)
 //                         fused: 1x1 conv on the re-quantised tile into acc2                     (acc2_full)
 //   warps 8-15   MID      (fused) acc1 -> +b7 -> snake2 -> bf16 hi[/lo] -> 64-channel A2 chunks  (a2_full)
-//   warps 16-19  STORE    acc -> +bias (+residual) -> y (fp32, HBM)
+//   warps 16-19  STORE    acc -> +bias (+residual) -> y (fp32, HBM) through a per-warp transposing stage
 //
 // Hand-offs are mbarriers; smem slots and TMEM accumulators are released by tcgen05.commit.  With two
 // accumulator stages (N <= 128) the MMA warp issues the K-tap conv of tile i+1 before the 1x1 conv of tile i,
@@ -34,7 +34,8 @@ constexpr int PROD_WARPS = 8;
 constexpr int MID_WARP0 = 8;
 constexpr int MID_WARPS = 8;
 constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 4;              // 8 (two per TMEM lane quarter, alternate 32-column blocks) measured slower: the
+                                          // register cap of the larger CTA (72) costs every role more than the stores gain
 constexpr int LOAD_WARP = EPI_WARP0 + EPI_WARPS;
 constexpr int MMA_WARP = LOAD_WARP + 1;
 constexpr int S_WARPS = MMA_WARP + 1;
@@ -63,7 +64,7 @@ struct SParams {
   const float* sib2;
   int B, T_in, T_out, C_in, C_out, K, stride, dil, pad_left, flags;
   int N, groups, tpu, upg, gpu1;
-  int slab_rows, rpp, NA, NB, acc_stages, acc_stride;
+  int slab_rows, rpp, NA, NB, acc_stages, acc_stride, epi_warps;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
   int tiles_per_item, tiles_per_nt, total_tiles;
   uint32_t idesc;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
   uint8_t* sB = sA + (size_t)p.a_stage * p.NA;
   uint8_t* sA2 = sB + (size_t)p.unit_bytes * p.NB;
   uint8_t* sStage = sA2 + (FUSE ? 2u * a2_chunk : 0u);   // EPI_WARPS x [32][EPI_LD] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * 32 * EPI_LD * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.epi_warps * 32 * EPI_LD * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
   uint32_t* s_off = tmem_slot + 2;   // [K + MAX_TPU] slab-row shift of tap k (16-byte units), padded for the unrolled issue block
   const uint32_t bar0 = smem_u32(bars);
@@ -105,11 +106,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_ACC1_FULL + s), 1);
-      mbar_init(BAR(B_ACC1_EMPTY + s), FUSE ? MID_WARPS : EPI_WARPS);
+      mbar_init(BAR(B_ACC1_EMPTY + s), FUSE ? MID_WARPS : p.epi_warps);
       mbar_init(BAR(B_A2_FULL + s), MID_WARPS);
       mbar_init(BAR(B_A2_EMPTY + s), 1);
       mbar_init(BAR(B_ACC2_FULL + s), 1);
-      mbar_init(BAR(B_ACC2_EMPTY + s), EPI_WARPS);
+      mbar_init(BAR(B_ACC2_EMPTY + s), p.epi_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -421,7 +422,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     // The accumulator arrives one row per lane; HBM wants whole lines.  Each warp owns a padded [32 rows][32 + 4]
     // fp32 staging block: the residual is fetched with 8 lanes per row (4 full lines per load instruction), lands in
     // the block, is combined in place by the lane that owns the row, and leaves the same coalesced way.
+    if (warp - EPI_WARP0 >= p.epi_warps) goto done;
     const int q = warp & 3;
+    const int cb0 = ((warp - EPI_WARP0) >> 2) * 32, cbstep = (p.epi_warps >> 2) * 32;   // this warp's 32-column blocks
     const bool tanh_out = (p.flags & BC_CONV_TANH_OUT) != 0;
     const float* bias = FUSE ? p.bias2 : p.bias;
     float* sT = reinterpret_cast<float*>(sStage) + (size_t)(warp - EPI_WARP0) * (32 * EPI_LD);
@@ -446,27 +449,27 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
       if (rp) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          res4[i] = 4 * i < rows_ok ? __ldg(reinterpret_cast<const float4*>(rp + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          res4[i] = 4 * i < rows_ok ? __ldg(reinterpret_cast<const float4*>(rp + cb0 + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      for (int c0 = cb0; c0 < p.N; c0 += cbstep) {
         if (rp) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(sT + (4 * i + crow) * EPI_LD + cchunk) = res4[i];
-          if (c0 + 32 < p.N) {   // next block's residual: in flight while this block is combined and stored
+          if (c0 + cbstep < p.N) {   // next block's residual: in flight while this block is combined and stored
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              res4[i] = 4 * i < rows_ok ? __ldg(reinterpret_cast<const float4*>(rp + c0 + 32 + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              res4[i] = 4 * i < rows_ok ? __ldg(reinterpret_cast<const float4*>(rp + c0 + cbstep + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           __syncwarp();
         }
-        if (c0 == 0) {
+        if (c0 == cb0) {
           mbar_wait(fullbar, (uint32_t)(ause & 1));
           tc_fence_after();
           if (warp == EPI_WARP0) STRACE(8);
         }
         uint32_t r[32];
         tmem_load32(taddr + (uint32_t)c0, r);
-        if (c0 + 32 >= p.N) {
+        if (c0 + cbstep >= p.N) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(emptybar);
@@ -513,7 +516,7 @@ done:
 long long* g_stream_trace = nullptr;
 
 struct StreamPlan {
-  int N, n_tiles, groups, tpu, upg, gpu1, slab_rows, rpp, NA, NB, acc_stages, acc_stride, tmem_cols, split;
+  int N, n_tiles, groups, tpu, upg, gpu1, slab_rows, rpp, NA, NB, acc_stages, acc_stride, tmem_cols, split, epi_warps;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
   size_t smem;
 };
@@ -551,20 +554,32 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   pl->a_stage = (uint32_t)((size_t)split * 2 * pl->plane_bytes + 127) & ~127u;
   if ((size_t)pl->plane_bytes * 2 >= (1u << 18)) return false;
   const size_t a2 = fused ? (size_t)2 * (A2_CH / 8) * A2_PLANE * split : 0;
-  const size_t misc = N_BARS * 8 + 64 + (32 + MAX_TPU) * 4 + (size_t)EPI_WARPS * 32 * EPI_LD * 4;
+  // eight store warps when the tile has at least two 32-column blocks and shared memory allows, else four
+  int epi_warps = (N >= 64 && EPI_WARPS >= 8) ? 8 : 4;
+  size_t misc = 0;
+  const size_t misc0 = N_BARS * 8 + 64 + (32 + MAX_TPU) * 4;
   const size_t budget = 225 * 1024;
   int NB = (int)(98304u / pl->unit_bytes);
   if (NB > 8) NB = 8;
   if (NB < 3) NB = 3;
   int NA = 0;
-  for (; NB >= 3; --NB) {
-    const size_t used = (size_t)NB * pl->unit_bytes + a2 + misc;
-    if (used >= budget) continue;
-    NA = (int)((budget - used) / pl->a_stage);
-    if (NA >= 2) break;
+  const int NB0 = NB;
+  for (; epi_warps >= 4; epi_warps -= 4) {   // prefer a full activation ring over the second set of store warps
+    misc = misc0 + (size_t)epi_warps * 32 * EPI_LD * 4;
+    for (NB = NB0; NB >= 3; --NB) {
+      const size_t used = (size_t)NB * pl->unit_bytes + a2 + misc;
+      if (used >= budget) continue;
+      NA = (int)((budget - used) / pl->a_stage);
+      if (NA >= 2) break;
+    }
+    const int want = pl->groups < 4 ? pl->groups : 4;
+    if (NB >= 3 && NA >= (want < 2 ? 2 : want)) break;
+    if (epi_warps == 4 && NB >= 3 && NA >= 2) break;
   }
+  if (epi_warps < 4) epi_warps = 4;
   if (NB < 3 || NA < 2) return false;
   if (NA > 4) NA = 4;
+  pl->epi_warps = epi_warps;
   pl->NA = NA;
   pl->NB = NB;
   pl->acc_stride = fused ? 2 * N : N;
@@ -581,7 +596,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
 int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) {
   p.N = pl.N; p.groups = pl.groups; p.tpu = pl.tpu; p.upg = pl.upg; p.gpu1 = pl.gpu1;
   p.slab_rows = pl.slab_rows; p.rpp = pl.rpp; p.NA = pl.NA; p.NB = pl.NB;
-  p.acc_stages = pl.acc_stages; p.acc_stride = pl.acc_stride; p.a_stage = pl.a_stage; p.unit_bytes = pl.unit_bytes;
+  p.acc_stages = pl.acc_stages; p.acc_stride = pl.acc_stride; p.epi_warps = pl.epi_warps; p.a_stage = pl.a_stage; p.unit_bytes = pl.unit_bytes;
   p.tap_bytes = pl.tap_bytes; p.tmem_cols = pl.tmem_cols; p.plane_bytes = pl.plane_bytes;
   p.tiles_per_item = (p.T_out + BM - 1) / BM;
   const long long per_nt = (long long)p.tiles_per_item * p.B;

@@ -25,8 +25,9 @@ _PRECISION = ["fp32"]
 LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
-STREAM_MIN_CIN = [64]   # ... when the layer has at least this many input channels (narrow layers: weights stay resident)
-STREAM_RU_MIN_C = [128]
+import os as _os
+STREAM_MIN_CIN = [int(_os.environ.get("BC_STREAM_MIN_CIN", "64"))]    # ... when the layer has at least this many input channels
+STREAM_RU_MIN_C = [int(_os.environ.get("BC_STREAM_RU_MIN_C", "128"))]  # ... ResidualUnits: narrower ones keep their weights resident (ru_persist)
 
 
 def _stream_tile(c_in, c_out, k, stride, dilation, precision, fused=False):

@@ -12,6 +12,7 @@ dil = int(sys.argv[3]) if len(sys.argv) > 3 else 9
 B, T = 8, 60000 * 128 // C
 if C == 256:
     T = 12000 * 4
+M.STREAM_RU_MIN_C[0] = 32
 ru = M.ResidualUnit(C, dilation=dil).cuda()
 x = torch.randn(B, T, C, device="cuda")
 M.set_precision(prec)
