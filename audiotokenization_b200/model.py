@@ -128,31 +128,40 @@ class BigCodecModel(nn.Module):
 
     def _extract_indices(self, wave_host, micro_batch, rnn_batch):
         dev = next(self.parameters()).device
-        N = wave_host.shape[0]
+        N, _, T = wave_host.shape
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         results = []
+        # two device staging buffers, filled on the copy stream while the other one is being encoded; explicit
+        # events instead of per-micro-batch allocations (no allocator traffic, no record_stream bookkeeping)
+        nbuf = 2
+        bufs = [torch.empty((micro_batch, T, 1), device=dev, dtype=torch.float32) for _ in range(nbuf)]
+        copied = [torch.cuda.Event() for _ in range(nbuf)]
+        consumed = [None] * nbuf
 
-        def stage(b0, b1):
+        def stage(i, b0, b1):
+            k = i % nbuf
             with torch.cuda.stream(copy_stream):
-                t = wave_host[b0:b1].to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return t, ev
+                if consumed[k] is not None:
+                    copy_stream.wait_event(consumed[k])
+                bufs[k][: b1 - b0].copy_(wave_host[b0:b1].view(b1 - b0, T, 1), non_blocking=True)
+                copied[k].record(copy_stream)
 
         spans = []
         for c0 in range(0, N, rnn_batch):
             c1 = min(N, c0 + rnn_batch)
             spans += [(b0, min(c1, b0 + micro_batch), min(c1, b0 + micro_batch) == c1) for b0 in range(c0, c1, micro_batch)]
-        nxt = stage(spans[0][0], spans[0][1]) if spans else None
+        if spans:
+            stage(0, spans[0][0], spans[0][1])
         feats = []
         for i, (b0, b1, last_of_group) in enumerate(spans):
-            xb, ev = nxt
-            main.wait_event(ev)
-            xb.record_stream(main)
+            k = i % nbuf
             if i + 1 < len(spans):
-                nxt = stage(spans[i + 1][0], spans[i + 1][1])
-            feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
+                stage(i + 1, spans[i + 1][0], spans[i + 1][1])
+            main.wait_event(copied[k])
+            feats.append(self.encoder.front_cl(bufs[k][: b1 - b0]))
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(main)
             if last_of_group:
                 feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
                 feats = []
