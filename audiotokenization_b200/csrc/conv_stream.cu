@@ -74,6 +74,20 @@ struct SParams {
   int dbg_bshift;   // timing experiment: copy only 1/2^n of every weight unit (results are wrong)
 };
 
+// 4 fp32 values -> bf16 hi (and lo = v - hi) halves of a 16-byte K-major row chunk
+template <int SPLIT>
+__device__ __forceinline__ void store_quad(const float4& v, uint8_t* d8, uint32_t lo_offset) {
+  uint2 h;
+  h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(d8) = h;
+  if (SPLIT == 2) {
+    uint2 l;
+    l.x = pack_bf16x2(v.x - __uint_as_float(h.x << 16), v.y - __uint_as_float(h.x & 0xffff0000u));
+    l.y = pack_bf16x2(v.z - __uint_as_float(h.y << 16), v.w - __uint_as_float(h.y & 0xffff0000u));
+    *reinterpret_cast<uint2*>(d8 + lo_offset) = l;
+  }
+}
+
 #define STRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
 #define STRACE_ADD(ev, v) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] += (v); } while (0)
 
@@ -91,7 +105,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
   uint8_t* sStage = sA2 + (FUSE ? 2u * a2_chunk : 0u);   // EPI_WARPS x [32][EPI_LD] fp32
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.epi_warps * 32 * EPI_LD * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
-  uint32_t* s_off = tmem_slot + 2;   // [K + MAX_TPU] slab-row shift of tap k (16-byte units), padded for the unrolled issue block
+  uint32_t* s_off = tmem_slot + 2;   // [32 + MAX_TPU] slab-row shift of tap k (16-byte units), padded for the unrolled issue block
+  float* sPar = reinterpret_cast<float*>(s_off + 32 + MAX_TPU + 2);   // fused: b7 | snake2 a | snake2 1/b | b1, N floats each (16-byte aligned)
   const uint32_t bar0 = smem_u32(bars);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
@@ -117,6 +132,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
   if (tid < 32 + MAX_TPU) {
     const int sh = min(tid, p.K - 1) * p.dil;
     s_off[tid] = (uint32_t)(sh % p.stride) * (uint32_t)p.rpp + (uint32_t)(sh / p.stride);
+  }
+  if (FUSE) {
+    for (int i = tid; i < p.N; i += S_THREADS) {
+      sPar[i] = __ldg(p.bias + i);
+      sPar[p.N + i] = __ldg(p.sa2 + i);
+      sPar[2 * p.N + i] = __ldg(p.sib2 + i);
+      sPar[3 * p.N + i] = __ldg(p.bias2 + i);
+    }
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -172,6 +195,41 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
         const float* xcol = xb + g * 16;
         uint8_t* dst = sA + (size_t)slot * p.a_stage + dst_off;
         bool waited = false;
+        if (p.stride == 1 && g0row >= 0 && g0row + p.slab_rows <= p.T_in && !(p.dbg_skip & 1)) {
+          // interior tile of an un-strided conv (almost every tile): no bounds tests, pointers advance by constants
+          const float* src = xcol + (size_t)(g0row + r_first) * p.C_in;
+          const size_t rstride = (size_t)rstep * p.C_in;
+          uint8_t* d8 = dst + (size_t)r_first * 16;
+          const uint32_t dstep = (uint32_t)rstep * 16u;
+          for (int r0 = r_first; r0 < p.slab_rows; r0 += rstep * P_BATCH, src += P_BATCH * rstride, d8 += P_BATCH * dstep) {
+            float4 v4[P_BATCH];
+#pragma unroll
+            for (int j = 0; j < P_BATCH; ++j)
+              if (r0 + rstep * j < p.slab_rows) v4[j] = __ldg(reinterpret_cast<const float4*>(src + j * rstride));
+            if (!waited) {
+              long long tw_ = p.trace ? clock64() : 0;
+              mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+              if (p.trace) wE += clock64() - tw_;
+              waited = true;
+            }
+#pragma unroll
+            for (int j = 0; j < P_BATCH; ++j) {
+              if (r0 + rstep * j < p.slab_rows) {
+                float4 v = v4[j];
+                if (snake) {
+                  if (SPLIT == 2) {
+                    v.x = snake_tc(v.x, sa.x, sb.x); v.y = snake_tc(v.y, sa.y, sb.y);
+                    v.z = snake_tc(v.z, sa.z, sb.z); v.w = snake_tc(v.w, sa.w, sb.w);
+                  } else {
+                    v.x = snake_bf(v.x, sa.x, sb.x); v.y = snake_bf(v.y, sa.y, sb.y);
+                    v.z = snake_bf(v.z, sa.z, sb.z); v.w = snake_bf(v.w, sa.w, sb.w);
+                  }
+                }
+                store_quad<SPLIT>(v, d8 + j * dstep, a_split);
+              }
+            }
+          }
+        } else
         for (int r0 = r_first; r0 < p.slab_rows && !(p.dbg_skip & 1); r0 += rstep * P_BATCH) {
           float4 v4[P_BATCH];
 #pragma unroll
@@ -203,16 +261,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
               }
               const int rr = p.stride == 1 ? r : (int)__umulhi((unsigned)r, inv_stride);   // exact for r < 2^16
               const int ph = r - rr * p.stride;
-              uint8_t* d8 = dst + ((size_t)ph * p.rpp + rr) * 16;
-              uint2 h;
-              h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(d8) = h;
-              if (SPLIT == 2) {
-                uint2 l;
-                l.x = pack_bf16x2(v.x - __uint_as_float(h.x << 16), v.y - __uint_as_float(h.x & 0xffff0000u));
-                l.y = pack_bf16x2(v.z - __uint_as_float(h.y << 16), v.w - __uint_as_float(h.y & 0xffff0000u));
-                *reinterpret_cast<uint2*>(d8 + a_split) = l;
-              }
+              store_quad<SPLIT>(v, dst + ((size_t)ph * p.rpp + rr) * 16, a_split);
             }
           }
         }
@@ -397,12 +446,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
 #pragma unroll
           for (int j = 0; j < ((p.dbg_skip & 2) ? 0 : 4); ++j) {
             const int ch = cbase + 8 * j;
-            const float4 bi0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-            const float4 bi1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + 1);
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.sa2 + ch));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.sa2 + ch) + 1);
-            const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.sib2 + ch));
-            const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.sib2 + ch) + 1);
+            const float4 bi0 = *reinterpret_cast<const float4*>(sPar + ch), bi1 = *reinterpret_cast<const float4*>(sPar + ch + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(sPar + p.N + ch), s1 = *reinterpret_cast<const float4*>(sPar + p.N + ch + 4);
+            const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch), i1 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch + 4);
             float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
                           __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
                           __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
@@ -479,7 +525,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
         for (int j = 0; j < 8; ++j) {
           float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                  __uint_as_float(r[4 * j + 3]));
-          if (bp) {
+          if (FUSE) {
+            const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * p.N + c0 + 4 * j);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          } else if (bp) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bp + c0) + j);
             v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
           }
@@ -557,7 +606,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   // eight store warps when the tile has at least two 32-column blocks and shared memory allows, else four
   int epi_warps = (N >= 64 && EPI_WARPS >= 8) ? 8 : 4;
   size_t misc = 0;
-  const size_t misc0 = N_BARS * 8 + 64 + (32 + MAX_TPU) * 4;
+  const size_t misc0 = N_BARS * 8 + 64 + (32 + MAX_TPU + 2) * 4 + 16 + (fused ? (size_t)4 * N * 4 : 0);
   const size_t budget = 225 * 1024;
   int NB = (int)(98304u / pl->unit_bytes);
   if (NB > 8) NB = 8;
