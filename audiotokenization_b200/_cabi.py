@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_int, c_size_t, c_void_p, POINTER
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbigcodec_b200.so")
+LIB_PATH = os.environ.get("BC_LIB_PATH") or os.path.join(_HERE, "libbigcodec_b200.so")   # BC_LIB_PATH: A/B builds of the same ABI
 
 BC_CONV_SNAKE_IN = 1
 BC_CONV_TANH_OUT = 2

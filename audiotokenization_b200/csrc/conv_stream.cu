@@ -32,7 +32,11 @@ constexpr int PROD_WARPS = 8;
 // eligible warps, and a delayed MMA-issue or weight-copy instruction idles the tensor core, while the
 // activation math of the producers has slack.
 constexpr int MID_WARP0 = 8;
-constexpr int MID_WARPS = 8;
+#ifndef BC_STREAM_MID_WARPS
+#define BC_STREAM_MID_WARPS 8
+#endif
+constexpr int MID_WARPS = BC_STREAM_MID_WARPS;   // 8: two per TMEM lane quarter (one 32-column half each); 4: one per quarter, both halves
+constexpr int MID_HALVES = 8 / MID_WARPS;
 constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;
 constexpr int EPI_WARPS = 4;              // 8 (two per TMEM lane quarter, alternate 32-column blocks) measured slower: the
                                           // register cap of the larger CTA (72) costs every role more than the stores gain
@@ -433,28 +437,32 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
         const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(q * 32) << 16);
         for (int c = 0; c < nchunk; ++c, ++a2seq) {
           const uint32_t s2 = a2seq & 1u, u2 = a2seq >> 1;
-          const int cbase = c * A2_CH + half * 32;
-          uint32_t r[32];
-          tmem_load32(taddr + (uint32_t)cbase, r);
-          if (c == nchunk - 1) {   // this warp's share of acc1 is in registers: hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(B_ACC1_EMPTY + as));
-          }
-          mbar_wait(BAR(B_A2_EMPTY + s2), (u2 & 1u) ^ 1u);
-          uint8_t* dst = sA2 + (size_t)s2 * a2_chunk + (size_t)(half * 4) * A2_PLANE + (size_t)row * 16;
 #pragma unroll
-          for (int j = 0; j < ((p.dbg_skip & 2) ? 0 : 4); ++j) {
-            const int ch = cbase + 8 * j;
-            const float4 bi0 = *reinterpret_cast<const float4*>(sPar + ch), bi1 = *reinterpret_cast<const float4*>(sPar + ch + 4);
-            const float4 s0 = *reinterpret_cast<const float4*>(sPar + p.N + ch), s1 = *reinterpret_cast<const float4*>(sPar + p.N + ch + 4);
-            const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch), i1 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch + 4);
-            float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
-                          __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
-                          __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
-                          __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
-            snake8<SPLIT>(v, s0, s1, i0, i1);
-            split_store<SPLIT>(v, dst + (size_t)j * A2_PLANE, a2_split);
+          for (int hh = 0; hh < MID_HALVES; ++hh) {
+            const int hcol = half + hh * (MID_WARPS / 4);        // 32-column half of the 64-channel chunk
+            const int cbase = c * A2_CH + hcol * 32;
+            uint32_t r[32];
+            tmem_load32(taddr + (uint32_t)cbase, r);
+            if (c == nchunk - 1 && hh == MID_HALVES - 1) {   // this warp's share of acc1 is in registers: hand the accumulator back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(B_ACC1_EMPTY + as));
+            }
+            if (hh == 0) mbar_wait(BAR(B_A2_EMPTY + s2), (u2 & 1u) ^ 1u);
+            uint8_t* dst = sA2 + (size_t)s2 * a2_chunk + (size_t)(hcol * 4) * A2_PLANE + (size_t)row * 16;
+#pragma unroll
+            for (int j = 0; j < ((p.dbg_skip & 2) ? 0 : 4); ++j) {
+              const int ch = cbase + 8 * j;
+              const float4 bi0 = *reinterpret_cast<const float4*>(sPar + ch), bi1 = *reinterpret_cast<const float4*>(sPar + ch + 4);
+              const float4 s0 = *reinterpret_cast<const float4*>(sPar + p.N + ch), s1 = *reinterpret_cast<const float4*>(sPar + p.N + ch + 4);
+              const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch), i1 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch + 4);
+              float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
+                            __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
+                            __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
+                            __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+              snake8<SPLIT>(v, s0, s1, i0, i1);
+              split_store<SPLIT>(v, dst + (size_t)j * A2_PLANE, a2_split);
+            }
           }
           fence_async_smem();
           __syncwarp();
