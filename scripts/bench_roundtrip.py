@@ -13,7 +13,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=64, help="clips per model() call; the whole batch by default so the LSTM runs once over it")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--layer-table", default=None)
     args = ap.parse_args()
