@@ -49,6 +49,7 @@ _SIGNATURES = {
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "bc_debug_set_ru_trace": (c_int, [c_void_p]),
     "bc_debug_set_stream_trace": (c_int, [c_void_p]),
+    "bc_debug_set_lstm_trace": (c_int, [c_void_p]),
     "bc_indices_to_int16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 

@@ -35,7 +35,10 @@ struct LstmTcParams {
   unsigned int* counters;  // [m_tiles]
   int B, T, H, NS, nslot, n_slices;
   uint32_t idesc;
+  long long* trace;   // debug: [step < 64][8] clock64 stamps of CTA (0,0), steps 100.. (NULL = off)
 };
+
+#define LTRACE(ev) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t >= 100 && t < 164) p.trace[(t - 100) * 8 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           } while (seen < target);
           asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
         }
+        LTRACE(0);
         const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
         for (int c = 0; c < nchunks; ++c, ++cc) {
           const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
             bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
                           src + (size_t)sp * (H / 8) * LM * 8 + (size_t)c * (KC / 8) * LM * 8, chunk_split, bar_full + 8u * slot);
         }
+        LTRACE(1);
       }
     }
   } else if (warp == 1) {
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
         }
         if (elect_one()) umma_commit(bar_accf);
         __syncwarp();
+        if (lane == 0) LTRACE(2);
       }
     }
   } else if (warp >= 4) {
@@ -179,6 +185,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
     for (int t = 0; t < p.T; ++t) {
       mbar_wait(bar_accf, (uint32_t)t & 1u);
       tc_fence_after();
+      if (gw == 0 && lane == 0) LTRACE(3);
       uint32_t acc[4][UPW];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -207,14 +214,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
         c_state[j] = c;
         hv[j] = sigmoid_acc(go) * tanh_acc(c);
       }
-      // next step's pre-activations: issued now, consumed after the next MMA phase
-      if (t + 1 < p.T) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < UPW; ++j) pg[g][j] = row_ok ? __ldcs(pre_row + (size_t)(t + 1) * 4 * H + (size_t)g * H + j) : 0.f;
-      }
-      // publish h_t (bf16 hi[/lo]) for the next step's MMA, in the UMMA K-major image
+      // publish h_t (bf16 hi[/lo]) for the next step's MMA, in the UMMA K-major image -- FIRST: every other CTA of
+      // this batch tile waits for it.  The fences below wait for all earlier memory operations of the thread, so
+      // nothing else (output store, skip load, next step's pre-activation loads) may be in flight before them.
       {
         __nv_bfloat16* dst = p.hx + (size_t)(t & 1) * hx_parity + hx_off;
         __nv_bfloat16 hi[UPW], lo[UPW];
@@ -230,6 +232,23 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(hi);
           if (SPLIT == 2) *reinterpret_cast<uint32_t*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint32_t*>(lo);
         }
+      }
+      // make the h stores visible (generic -> async proxy, gpu scope), then one release-increment per CTA
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __threadfence();
+      if (gw == 0 && lane == 0) LTRACE(4);
+      asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
+      if (gw == 0 && lane == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + m) : "memory");
+        LTRACE(5);
+      }
+      // off the critical path (overlaps the other CTAs' publishes, the h copies and the next MMA phase):
+      // next step's pre-activations and this step's output row
+      if (t + 1 < p.T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int j = 0; j < UPW; ++j) pg[g][j] = row_ok ? __ldcs(pre_row + (size_t)(t + 1) * 4 * H + (size_t)g * H + j) : 0.f;
       }
       if (row_ok) {
         const size_t o = out_row + (size_t)t * H;
@@ -249,12 +268,6 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           __stcs(reinterpret_cast<float2*>(p.y + o), v);
         }
       }
-      // make the h stores visible (generic -> async proxy, gpu scope), then one release-increment per CTA
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
-      if (gw == 0 && lane == 0)
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + m) : "memory");
     }
   }
   tc_fence_before();
@@ -263,6 +276,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NS < 32 ? 32 : NS)) : "memory");
   }
 }
+
+long long* g_lstm_trace = nullptr;
 
 struct LstmTcPlan {
   int NS, nslot, n_slices, m_tiles, split;
@@ -331,6 +346,7 @@ extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, c
   if (pl.n_slices * pl.m_tiles > sms)
     return bc::fail(BC_EUNSUPPORTED, "lstm_tc: B=%d needs %d co-resident CTAs, device has %d SMs (split the batch)", B, pl.n_slices * pl.m_tiles, sms);
   LstmTcParams p;
+  p.trace = g_lstm_trace;
   p.pre = pre; p.wimg = reinterpret_cast<const uint4*>(w_image); p.skip = skip; p.y = y;
   p.hx = reinterpret_cast<__nv_bfloat16*>(workspace);
   p.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + ((pl.hx_bytes + 127) & ~size_t(127)));
@@ -344,5 +360,11 @@ extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, c
   void* args[] = {(void*)&p};
   e = cudaLaunchCooperativeKernel(kern, dim3(pl.n_slices, pl.m_tiles), dim3(L_THREADS), args, pl.smem, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaLaunchCooperativeKernel(lstm_tc)");
+  return BC_OK;
+}
+
+// debug hook (not part of the product path): device buffer of 64*8 int64 receiving clock64 stamps of CTA (0,0)
+extern "C" int bc_debug_set_lstm_trace(void* device_buffer) {
+  g_lstm_trace = reinterpret_cast<long long*>(device_buffer);
   return BC_OK;
 }

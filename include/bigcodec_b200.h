@@ -211,6 +211,8 @@ int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_str
 int bc_debug_set_ru_trace(void* device_buffer);
 /* same for the streamed-weight kernel (events: producer, MMA, MID, store stamps and MMA-warp wait totals) */
 int bc_debug_set_stream_trace(void* device_buffer);
+/* tensor-core LSTM: [64 steps][8] stamps (counter seen, h copies issued, MMAs issued, gates start, h stored, published) */
+int bc_debug_set_lstm_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

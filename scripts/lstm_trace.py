@@ -24,3 +24,25 @@ for prec in ("bf16", "bf16x3"):
         ms = e0.elapsed_time(e1)
         print(f"{prec:7s} B={B:4d}: {ms:7.2f} ms  {ms / T * 1e3:6.2f} us/step  max_batch {mb}")
         del pre, y
+
+# per-phase timeline of CTA (0,0), steps 100..163 (B = 256, split precision)
+from audiotokenization_b200 import _cabi
+lib = _cabi.load_library()
+for prec, B in (("bf16x3", 256), ("bf16x3", 64), ("bf16", 256)):
+    lstm = M.ResLSTM(H, num_layers=1).cuda()
+    img = lstm.lstm.recurrent_image_for(0, prec)
+    mb = ops.lstm_tc_max_batch(H, prec)
+    pre = torch.randn(B, T, 4 * H, device="cuda") * 0.5
+    ops.lstm_recurrent_tc(pre, img, None, prec, mb)
+    torch.cuda.synchronize()
+    trace = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
+    lib.bc_debug_set_lstm_trace(trace.data_ptr())
+    ops.lstm_recurrent_tc(pre, img, None, prec, mb)
+    torch.cuda.synchronize()
+    lib.bc_debug_set_lstm_trace(None)
+    t = trace.cpu().view(64, 8).double()
+    names = ["counter seen", "h copies issued", "MMAs issued", "gates start (acc ready)", "h stored+fenced", "published"]
+    step = (t[1:, 5] - t[:-1, 5]).mean()
+    print(f"{prec} B={B}: {step:.0f} cycles per step; phase offsets from the previous step's publish:")
+    for j, n in enumerate(names):
+        print(f"   {n:28s} {float((t[1:, j] - t[:-1, 5]).mean()):8.0f}")
