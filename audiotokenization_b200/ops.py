@@ -27,8 +27,8 @@ def _count(n: int = 1) -> None:
 
 
 class _Timed:
-    def __init__(self, kind, flops, device):
-        self.kind, self.flops, self.device = kind, flops, device
+    def __init__(self, kind, flops, device, kernel="?", nbytes=0.0):
+        self.kind, self.flops, self.device, self.kernel, self.nbytes = kind, flops, device, kernel, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -40,7 +40,7 @@ class _Timed:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record(torch.cuda.current_stream(self.device))
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.kernel, self.nbytes))
         return False
 
 
@@ -122,7 +122,9 @@ def conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, st
         res = _cl(res, "res")
         if tuple(res.shape) != (B, t_out, C_out):
             raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, C_out)}")
-    with _Timed(("conv1d", C_in, C_out, K, stride, dilation, t_out, B, precision), 2.0 * B * t_out * C_out * C_in * K, x.device):
+    with _Timed(("conv1d", C_in, C_out, K, stride, dilation, t_out, B, precision), 2.0 * B * t_out * C_out * C_in * K, x.device,
+                "conv1d_f32_kernel" if precision == "fp32" else "conv1d_tc_kernel",
+                4.0 * B * (T_in * C_in + t_out * C_out * (2 if res is not None else 1))):
         check(load_library().bc_conv1d_fwd(ptr(x), ptr(w), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res), ptr(y),
                                            B, T_in, C_in, t_out, C_out, K, stride, dilation, pad_left,
                                            t_out, 1, 0, flags, PRECISIONS[precision], stream_ptr(x.device)),
@@ -138,7 +140,9 @@ def resunit(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, 
     B, T, C = x.shape
     y = torch.empty_like(x)
     flops = 2.0 * B * T * C * C * (k + 1)
-    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device):
+    plan = resunit_plan(C, k, dilation, precision)
+    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device,
+                "ru_persist_kernel" if (plan and plan[1]) else "conv1d_tc_kernel", 8.0 * B * T * C):
         check(load_library().bc_resunit_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1), ptr(sa2),
                                             ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left, PRECISIONS[precision],
                                             stream_ptr(x.device)), "bc_resunit_fwd")
@@ -167,7 +171,8 @@ def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[tor
     y = torch.empty((B, T_in * stride, C_out), device=x.device, dtype=torch.float32)
     flags = BC_CONV_SNAKE_IN if snake_a is not None else 0
     with _Timed(("convtr1d", C_in, C_out, 2 * stride, stride, 1, T_in * stride, B, precision),
-                2.0 * B * T_in * stride * C_out * C_in * 2, x.device):
+                2.0 * B * T_in * stride * C_out * C_in * 2, x.device,
+                "conv1d_f32_kernel" if precision == "fp32" else "conv1d_tc_kernel", 4.0 * B * T_in * (C_in + stride * C_out)):
         check(load_library().bc_convtr1d_fwd(ptr(x), ptr(w_phases), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(y),
                                              B, T_in, C_in, C_out, stride, padding, flags, PRECISIONS[precision],
                                              stream_ptr(x.device)), "bc_convtr1d_fwd")
@@ -268,7 +273,8 @@ def conv1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Ten
         res = _cl(res, "res")
         if tuple(res.shape) != (B, t_out, c_out):
             raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, c_out)}")
-    with _Timed(("conv1d", C_in, c_out, k, stride, dilation, t_out, B, precision), 2.0 * B * t_out * c_out * C_in * k, x.device):
+    with _Timed(("conv1d", C_in, c_out, k, stride, dilation, t_out, B, precision), 2.0 * B * t_out * c_out * C_in * k, x.device,
+                "conv_stream_kernel", 4.0 * B * (T_in * C_in + t_out * c_out * (2 if res is not None else 1))):
         check(load_library().bc_conv1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res),
                                                   ptr(y), B, T_in, C_in, t_out, c_out, k, stride, dilation, pad_left,
                                                   flags, PRECISIONS[precision], stream_ptr(x.device)),
@@ -284,7 +290,7 @@ def resunit_stream(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.T
     B, T, C = x.shape
     y = torch.empty_like(x)
     flops = 2.0 * B * T * C * C * (k + 1)
-    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device):
+    with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device, "conv_stream_kernel", 8.0 * B * T * C):
         check(load_library().bc_resunit_stream_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1),
                                                    ptr(sa2), ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left,
                                                    PRECISIONS[precision], stream_ptr(x.device)),
@@ -308,7 +314,7 @@ def lstm_recurrent(pre: torch.Tensor, w_hh_packed: torch.Tensor, skip: Optional[
     for b0 in range(0, B, LSTM_MAX_BATCH):
         b1 = min(B, b0 + LSTM_MAX_BATCH)
         ws = torch.empty(lib.bc_lstm_workspace_bytes(b1 - b0, H), device=pre.device, dtype=torch.uint8)
-        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, "fp32"), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
+        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, "fp32"), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device, "lstm_rec_kernel"):
             check(lib.bc_lstm_recurrent_fwd(ptr(pre[b0:b1]), ptr(w_hh_packed),
                                             ptr(skip[b0:b1]) if skip is not None else None,
                                             ptr(y[b0:b1]), ptr(ws), b1 - b0, T, H, stream_ptr(pre.device)),
@@ -355,7 +361,7 @@ def lstm_recurrent_tc(pre: torch.Tensor, w_image: torch.Tensor, skip: Optional[t
         b1 = min(B, b0 + max_batch)
         ws = torch.empty(lib.bc_lstm_tc_workspace_bytes(b1 - b0, H, PRECISIONS[precision]), device=pre.device,
                          dtype=torch.uint8)
-        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, precision), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device):
+        with _Timed(("lstm", H, H, 0, 0, 0, T, b1 - b0, precision), 2.0 * (b1 - b0) * T * 4 * H * H, pre.device, "lstm_tc_kernel"):
             check(lib.bc_lstm_tc_recurrent_fwd(ptr(pre[b0:b1]), ptr(w_image),
                                                ptr(skip[b0:b1]) if skip is not None else None, ptr(y[b0:b1]), ptr(ws),
                                                b1 - b0, T, H, PRECISIONS[precision], stream_ptr(pre.device)),

@@ -274,32 +274,72 @@ def main():
     step_device()
     torch.cuda.synchronize(dev)
     prof, ops.PROFILE = ops.PROFILE, None
-    by_kind, by_layer = {}, {}
-    for key, flops, a, b in prof:
+    by_kind, by_layer, by_kernel = {}, {}, {}
+    for key, flops, a, b, kernel, nbytes in prof:
         ms = a.elapsed_time(b)
-        for table, k in ((by_kind, key[0]), (by_layer, key)):
-            d = table.setdefault(k, [0.0, 0.0, 0])
+        for table, k in ((by_kind, key[0]), (by_layer, key), (by_kernel, kernel)):
+            d = table.setdefault(k, [0.0, 0.0, 0, 0.0])
             d[0] += flops
             d[1] += ms
             d[2] += 1
+            d[3] += nbytes
     if args.layer_table and rank == 0:
         with open(args.layer_table, "w") as f:
             f.write("| kind | C_in | C_out | K | stride | dil | T_out | B | prec | launches | ms/step | TFLOP/s |\n"
                     "|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
-            for k, (fl, ms, n) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
+            for k, (fl, ms, n, _) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
                 f.write("| " + " | ".join(str(v) for v in k) + f" | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} |\n")
+            f.write("\n| kernel | launches | ms/step | TFLOP/s | algorithmic GB/s |\n|---|---:|---:|---:|---:|\n")
+            for k, (fl, ms, n, nb) in sorted(by_kernel.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"| `{k}` | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} | {nb / ms / 1e6 if ms else 0:.0f} |\n")
     CONV_KINDS = ("conv1d", "convtr1d", "resunit")
     conv_flops = sum(v[0] for k, v in by_kind.items() if k in CONV_KINDS)
     conv_ms = sum(v[1] for k, v in by_kind.items() if k in CONV_KINDS)
     step_ms = ms_total / args.steps
     peaks = load_peaks()
-    achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv1d / fused ResidualUnit (dense contractions incl. LSTM input projection)",
-                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
-                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                "launches_per_step": sum(v[2] for k, v in by_kind.items() if k in CONV_KINDS),
-                "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms if step_ms else None,
+    # dominant kernel = the tcgen05 convolution kernel family with the largest share of the step
+    conv_kernels = {k: v for k, v in by_kernel.items() if k in ("conv_stream_kernel", "ru_persist_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel")}
+    dom = max(conv_kernels, key=lambda k: conv_kernels[k][1]) if conv_kernels else None
+    d_fl, d_ms, d_n, d_bytes = conv_kernels[dom] if dom else (0.0, 0.0, 0, 0.0)
+    # which roof bounds it: arithmetic intensity of its launches against the ridge of the measured peaks
+    ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    intensity = d_fl / d_bytes if d_bytes > 0 else float("inf")
+    hbm_bound = intensity < ridge
+    tflops = d_fl / (d_ms / 1000.0) / 1e12 if d_ms > 0 else 0.0
+    gbs = d_bytes / (d_ms / 1000.0) / 1e9 if d_ms > 0 else 0.0
+    traffic = None
+    try:   # average DRAM bytes per launch of that kernel from the committed ncu pass (profiles/, same launch shapes)
+        with open(os.path.join(REPO, "profiles", "kernel_traffic.json")) as f:
+            traffic = json.load(f).get(args.precision, {}).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        traffic = None
+
+    def kernel_entry(v):
+        fl, ms, n, nb = v
+        return {"launches": n, "ms_per_step": ms, "tflops": fl / ms / 1e9 if ms else 0.0,
+                "algorithmic_gbs": nb / ms / 1e6 if ms else 0.0, "flop_per_byte": fl / nb if nb else None,
+                "share_of_step": ms / step_ms if step_ms else None}
+
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
+                "achieved": gbs if hbm_bound else tflops,
+                "peak": peaks["hbm_gbs"] if hbm_bound else peaks["bf16_tflops_sustained"],
+                "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": (gbs / peaks["hbm_gbs"]) if hbm_bound else (tflops / peaks["bf16_tflops_sustained"]),
+                "traffic": traffic,
+                "peak_source": f"{peaks['source']} ({'copy bandwidth' if hbm_bound else 'bf16 sustained'}, kernel timed inside a long step)",
+                "definition": "dominant kernel = tcgen05 conv kernel family with the largest share of the step; algorithmic bytes "
+                              "(fp32 activation read once + written once) or FLOPs (2*MAC, bf16x3 counted once) of its launches in "
+                              "one instrumented step / their CUDA-event time on the launch stream; bound chosen by the launches' "
+                              f"FLOP/byte ({intensity:.0f}) against the ridge of the measured peaks ({ridge:.0f})",
+                "launches_per_step": d_n, "avg_launch_ms": d_ms / d_n if d_n else None,
+                "algorithmic_bytes_per_launch": d_bytes / d_n if d_n else None,
+                "flop_per_launch": d_fl / d_n if d_n else None, "tflops": tflops,
+                "tensor_frac": tflops / peaks["bf16_tflops_sustained"],
+                "kernel_ms_per_step": d_ms, "share_of_step": d_ms / step_ms if step_ms else None,
+                "all_kernels": {k: kernel_entry(v) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
+                "dense_contractions": {"tflops": conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0,
+                                       "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms if step_ms else None,
+                                       "tensor_frac": conv_flops / (conv_ms / 1000.0) / 1e12 / peaks["bf16_tflops_sustained"] if conv_ms > 0 else 0.0},
                 "lstm_ms_per_step": by_kind.get("lstm", [0, 0, 0])[1],
                 "whole_step_frac": (value / world) * ENC_GFLOP_PER_AUDIO_S.get(args.model, 0.0) / 1e3
                 / peaks["bf16_tflops_sustained"]}

@@ -57,7 +57,7 @@ def main():
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         by = {}
-        for key, fl, a, b in prof:
+        for key, fl, a, b, _kernel, _nbytes in prof:
             d = by.setdefault(key, [0.0, 0.0, 0]); d[0] += fl; d[1] += a.elapsed_time(b); d[2] += 1
         with open(args.layer_table, "w") as f:
             f.write("| kind | C_in | C_out | K | stride | dil | T_out | B | prec | launches | ms/step | TFLOP/s |\n|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")

@@ -3,6 +3,7 @@
 
   summarize_ncu.py launches <launches.csv> <out.md>        per-kernel launch count / time / share
   summarize_ncu.py full <prof.ncu-rep> <out.md>            key metrics of each profiled launch
+  summarize_ncu.py traffic <dram.csv> <out.json> <prec>    average DRAM bytes per launch per kernel family
 """
 import collections
 import csv
@@ -78,5 +79,47 @@ def full(path, out):
     print(open(out).read()[:6000])
 
 
+def traffic(path, out_json, precision):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv log -> per-kernel-family
+    average DRAM bytes per launch, merged into profiles/kernel_traffic.json under `precision`."""
+    import json, os
+    rows = [l for l in open(path) if l.startswith('"')]
+    rd = csv.DictReader(io.StringIO("".join(rows)))
+    agg = {}
+    for r in rd:
+        name = r["Kernel Name"]
+        fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel", "lstm_tc_kernel",
+                                "stem_conv_kernel", "vq_encode_kernel") if f in name), None)
+        if fam is None:
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6}.get(unit, 1.0)
+        a = agg.setdefault(fam, {"launch_ids": set(), "rd": 0.0, "wr": 0.0, "ns": 0.0})
+        a["launch_ids"].add(r["ID"])
+        if r["Metric Name"] == "dram__bytes_read.sum":
+            a["rd"] += v * scale
+        elif r["Metric Name"] == "dram__bytes_write.sum":
+            a["wr"] += v * scale
+        elif r["Metric Name"] == "gpu__time_duration.sum":
+            a["ns"] += v * scale
+    res = {}
+    for fam, a in agg.items():
+        n = len(a["launch_ids"])
+        res[fam] = {"launches": n, "dram_bytes_per_launch": (a["rd"] + a["wr"]) / n, "dram_read_per_launch": a["rd"] / n,
+                    "dram_write_per_launch": a["wr"] / n, "ncu_us_per_launch": a["ns"] / n / 1e3}
+    cur = {}
+    if os.path.exists(out_json):
+        cur = json.load(open(out_json))
+    cur[precision] = res
+    cur["_how"] = ("ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over "
+                   "`bench.py --clips-per-gpu 8 --steps 1` (micro-batch 8: the launch shapes of the full bench's conv kernels)")
+    json.dump(cur, open(out_json, "w"), indent=1, sort_keys=True)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
