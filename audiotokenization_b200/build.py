@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + (["-DBC_TRACE"] if os.environ.get("BC_TRACE") == "1" else [])   # per-stage clock stamps for scripts/*_trace.py
 
 
 def _sources():

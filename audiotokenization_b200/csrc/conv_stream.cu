@@ -92,8 +92,33 @@ __device__ __forceinline__ void store_quad(const float4& v, uint8_t* d8, uint32_
   }
 }
 
+// (n-tile, item, tile-in-item) of a CTA's current tile, advanced incrementally: the tile loop has no division
+struct TilePos {
+  int nt, b, tt;
+  __device__ __forceinline__ void init(int tile, int tiles_per_item, int B) {
+    const int per_nt = tiles_per_item * B;
+    nt = tile / per_nt;
+    const int rem = tile - nt * per_nt;
+    b = rem / tiles_per_item;
+    tt = rem - b * tiles_per_item;
+  }
+  __device__ __forceinline__ void advance(int inc, int tiles_per_item, int B) {
+    tt += inc;
+    while (tt >= tiles_per_item) {
+      tt -= tiles_per_item;
+      if (++b == B) { b = 0; ++nt; }
+    }
+  }
+};
+
+// stage stamps are compiled in only with -DBC_TRACE (BC_TRACE=1 python -m audiotokenization_b200.build)
+#ifdef BC_TRACE
 #define STRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
-#define STRACE_ADD(ev, v) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] += (v); } while (0)
+#define STRACE_ON (p.trace != nullptr)
+#else
+#define STRACE(ev) do { } while (0)
+#define STRACE_ON false
+#endif
 
 template <int SPLIT, bool FUSE>
 __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams p) {
@@ -179,10 +204,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     const uint32_t dst_off = (uint32_t)(c4 >> 1) * plane_bytes + (uint32_t)(c4 & 1) * 8u;
     int it = 0;
     int slot_c = 0, use_c = 0, sq = 0;   // running ring position over ALL stages (every team counts every stage)
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
-      const int rem = tile % p.tiles_per_nt;
-      const int b = rem / p.tiles_per_item;
-      const int t0 = (rem - b * p.tiles_per_item) * BM;
+    TilePos tp;
+    tp.init(first, p.tiles_per_item, p.B);
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it, tp.advance(step, p.tiles_per_item, p.B)) {
+      const int b = tp.b;
+      const int t0 = tp.tt * BM;
       const int g0row = t0 * p.stride - p.pad_left;
       const float* xb = p.x + (size_t)b * p.T_in * p.C_in + c4 * 4;
       long long wE = 0;
@@ -211,9 +237,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
             for (int j = 0; j < P_BATCH; ++j)
               if (r0 + rstep * j < p.slab_rows) v4[j] = __ldg(reinterpret_cast<const float4*>(src + j * rstride));
             if (!waited) {
-              long long tw_ = p.trace ? clock64() : 0;
+              long long tw_ = STRACE_ON ? clock64() : 0;
               mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
-              if (p.trace) wE += clock64() - tw_;
+              if (STRACE_ON) wE += clock64() - tw_;
               waited = true;
             }
 #pragma unroll
@@ -244,9 +270,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
             else v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (!waited) {   // the loads above are in flight while we wait for the slot
-            long long tw_ = p.trace ? clock64() : 0;
+            long long tw_ = STRACE_ON ? clock64() : 0;
             mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
-            if (p.trace) wE += clock64() - tw_;
+            if (STRACE_ON) wE += clock64() - tw_;
             waited = true;
           }
 #pragma unroll
@@ -275,19 +301,21 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
         if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
         if (g == p.groups - 1 && tw == 0) STRACE(1);
       }
-      if (p.trace && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) p.trace[it * 16 + 12] = wE;
+      if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) p.trace[it * 16 + 12] = wE;
     }
   } else if (warp == LOAD_WARP) {
     // ======================= WEIGHTS: unit ring, same order as the MMA warp consumes =======================
     if (lane == 0 && !freerun && !free_b) {
       uint32_t slot = 0, phase = 1;   // ring position; `phase` = parity a free slot's empty barrier must have completed
+      TilePos ltp;
+      ltp.init(first, p.tiles_per_item, p.B);
       const uint32_t uB = smem_u32(sB);
       const int nchunk = p.N / A2_CH;
       const int last = defer ? n_my : n_my - 1;
       for (int it = 0; it <= last; ++it) {
         if (it < n_my) {
-          const int tile = first + it * step;
-          const int nt = tile / p.tiles_per_nt;
+          const int nt = ltp.nt;
+          ltp.advance(step, p.tiles_per_item, p.B);
           const uint8_t* wnt = p.w7 + (size_t)nt * p.groups * p.K * p.tap_bytes;
           for (int g = 0; g < p.groups; ++g)
             for (int u = 0; u < p.upg; ++u) {
@@ -484,12 +512,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     float* sT = reinterpret_cast<float*>(sStage) + (size_t)(warp - EPI_WARP0) * (32 * EPI_LD);
     const int crow = lane >> 3, cchunk = (lane & 7) * 4;          // coalesced mapping: rows crow + 4*i, 4 floats at cchunk
     int it = 0;
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+    TilePos tp;
+    tp.init(first, p.tiles_per_item, p.B);
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it, tp.advance(step, p.tiles_per_item, p.B)) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
-      const int nt = tile / p.tiles_per_nt;
-      const int rem = tile - nt * p.tiles_per_nt;
-      const int b = rem / p.tiles_per_item;
-      const int trow0 = (rem - b * p.tiles_per_item) * BM + q * 32;     // first output row of this warp's block
+      const int nt = tp.nt, b = tp.b;
+      const int trow0 = tp.tt * BM + q * 32;     // first output row of this warp's block
       const size_t off0 = ((size_t)b * p.T_out + trow0 + crow) * p.C_out + (size_t)nt * p.N + cchunk;
       const float* rp = (p.res && !(p.dbg_skip & 4)) ? p.res + off0 : nullptr;
       float* yp = p.y + off0;

@@ -38,7 +38,11 @@ struct LstmTcParams {
   long long* trace;   // debug: [step < 64][8] clock64 stamps of CTA (0,0), steps 100.. (NULL = off)
 };
 
+#ifdef BC_TRACE
 #define LTRACE(ev) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t >= 100 && t < 164) p.trace[(t - 100) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define LTRACE(ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {

@@ -55,7 +55,16 @@ struct RuParams {
   long long* trace;   // debug: [tile_it < 64][16 events] clock64 stamps of CTA 0 (NULL = off)
 };
 
+// per-stage clock stamps are compiled in only with -DBC_TRACE (python -m audiotokenization_b200.build with BC_TRACE=1):
+// the tiles of the narrow layers are so short that even the disabled checks were ~7 % of the executed instructions
+#ifdef BC_TRACE
 #define TRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(ev) do { } while (0)
+#endif
+// ring slot / use count of pipeline step `i` for nslot in {1, 2} without a runtime division
+#define SLOT_OF(i) (p.nslot == 2 ? ((i) & 1) : 0)
+#define USE_OF(i) (p.nslot == 2 ? ((i) >> 1) : (i))
 
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
        B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
@@ -139,10 +148,12 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.sib1 + pl * 8));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.sib1 + pl * 8) + 1);
     int it = grp;
-    for (int tile = first + grp * step; tile < p.total_tiles; tile += ngroups * step, it += ngroups) {
-      const int slot = it % p.nslot, use = it / p.nslot;
-      const int b = tile / p.tiles_per_item;
-      const int g0 = (tile - b * p.tiles_per_item) * BM - p.pad_left;
+    // (item, tile-in-item) advance incrementally: one division per CTA instead of one per tile
+    int b = (first + grp * step) / p.tiles_per_item, tt = (first + grp * step) - b * p.tiles_per_item;
+    for (int tile = first + grp * step; tile < p.total_tiles; tile += ngroups * step, it += ngroups, tt += ngroups * step) {
+      while (tt >= p.tiles_per_item) { tt -= p.tiles_per_item; ++b; }
+      const int slot = SLOT_OF(it), use = USE_OF(it);
+      const int g0 = tt * BM - p.pad_left;
       const float* xcol = p.x + (size_t)b * p.T * C + pl * 8;
       uint8_t* dstA = sA + (size_t)slot * a_slot + (size_t)pl * plane_bytes;
       bool waited = false;
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       const uint32_t a2_g = (2u * a2_plane) >> 4;
       for (int it = 0; it <= n_my; ++it) {
         if (it < n_my) {  // K-tap conv of tile `it`
-          const int slot = it % p.nslot, use = it / p.nslot, as = it & 1, ause = it >> 1;
+          const int slot = SLOT_OF(it), use = USE_OF(it), as = it & 1, ause = it >> 1;
           mbar_wait(BAR(B_A_FULL + slot), (uint32_t)(use & 1));
           mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
@@ -232,7 +243,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
         }
         if (it >= 1) {  // 1x1 conv of tile `it - 1`
           const int j = it - 1;
-          const int slot = j % p.nslot, use = j / p.nslot, as = j & 1, ause = j >> 1;
+          const int slot = SLOT_OF(j), use = USE_OF(j), as = j & 1, ause = j >> 1;
           mbar_wait(BAR(B_A2_FULL + slot), (uint32_t)(use & 1));
           mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     const int cbeg = chalf * (C / 2), cend = cbeg + C / 2;
     int it = 0;
     for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
-      const int slot = it % p.nslot, use = it / p.nslot, as = it & 1, ause = it >> 1;
+      const int slot = SLOT_OF(it), use = USE_OF(it), as = it & 1, ause = it >> 1;
       mbar_wait(BAR(B_ACC1_FULL + as), (uint32_t)(ause & 1));
       tc_fence_after();
       mbar_wait(BAR(B_A2_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
@@ -307,10 +318,11 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     // ======================= STORE: acc2 + b1 + x -> y =======================
     const int q = warp & 3;
     int it = 0;
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
+    int b = first / p.tiles_per_item, tt = first - b * p.tiles_per_item;
+    for (int tile = first; tile < p.total_tiles; tile += step, ++it, tt += step) {
+      while (tt >= p.tiles_per_item) { tt -= p.tiles_per_item; ++b; }
       const int as = it & 1, ause = it >> 1;
-      const int b = tile / p.tiles_per_item;
-      const int t = (tile - b * p.tiles_per_item) * BM + q * 32 + lane;
+      const int t = tt * BM + q * 32 + lane;
       const bool row_ok = t < p.T;
       const size_t off = ((size_t)b * p.T + (row_ok ? t : 0)) * C;
       const float* rp = p.x + off;
