@@ -32,7 +32,10 @@ constexpr int GROUP_WARPS = LOAD_WARPS / LOAD_GROUPS;
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 constexpr int MMA_WARP = 8;
 constexpr int MID_WARP0 = 9;                        // 8 warps: 2 per TMEM lane quarter (column halves)
-constexpr int MID_WARPS = 8;
+#ifndef BC_RU_MID_WARPS
+#define BC_RU_MID_WARPS 4
+#endif
+constexpr int MID_WARPS = BC_RU_MID_WARPS;   // 4 (one per TMEM lane quarter) measured 5-13 % faster than 8: 544 threads leave 96+ registers per thread, no spills
 constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;    // 4 warps
 constexpr int RU_WARPS = EPI_WARP0 + 4;
 constexpr int RU_THREADS = RU_WARPS * 32;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int chalf = (warp - MID_WARP0) >> 2;       // which half of the channels this warp converts
-    const int cbeg = chalf * (C / 2), cend = cbeg + C / 2;
+    const int cbeg = chalf * (C / (MID_WARPS / 4)), cend = cbeg + C / (MID_WARPS / 4);
     int it = 0;
     for (int tile = first; tile < p.total_tiles; tile += step, ++it) {
       const int slot = SLOT_OF(it), use = USE_OF(it), as = it & 1, ause = it >> 1;
