@@ -207,6 +207,17 @@ int bc_vq_dequant(const int32_t* idx, const float* cb, const float* w_out, const
 /* int32 [n_q][N] indices -> int16 [N][n_q], the on-disk layout of extract_indices.py:520-532. */
 int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_stream_t s);
 
+/* ---- codebook statistics ---------------------- */
+/* Replaces the index bookkeeping of CodebookPerplexity.update / CodebookUtilization.update
+ * (lightning_module.py:33-36,62-64: one-hot sum / used-code mask) and the Counter of inference_full.py:570-604:
+ *   counts[c] += #{n < N : idx[n] == c}      (uint64, DEVICE, accumulating: zero it before the first call)
+ * Indices outside [0, Kc) are counted into *bad_count (optional device int) and ignored. */
+int bc_code_histogram(const int32_t* idx, long long N, int Kc, unsigned long long* counts, int* bad_count, bc_stream_t s);
+/* out3[0] = entropy in nats of counts/sum(counts) over the used codes (CodebookPerplexity.compute,
+ * lightning_module.py:38-51, before the exp), out3[1] = number of used codes (CodebookUtilization.compute,
+ * :66-69, before the division), out3[2] = sum(counts).  out3: 3 doubles, DEVICE. */
+int bc_code_entropy(const unsigned long long* counts, int Kc, double* out3, bc_stream_t s);
+
 /* debug only: per-stage clock64 stamps of the persistent ResidualUnit kernel (CTA 0, first 64 tiles) */
 int bc_debug_set_ru_trace(void* device_buffer);
 /* same for the streamed-weight kernel (events: producer, MMA, MID, store stamps and MMA-warp wait totals) */

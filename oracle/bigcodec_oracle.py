@@ -358,3 +358,72 @@ def indices_to_int16(indices: Tensor):
         idx = idx.permute(1, 0)
     arr = idx.cpu().numpy().astype(np.int16)
     return arr
+
+
+# ----------------------------------------------------------------------------
+# the steps on either side of the hot path (codebook statistics, on-disk layout)
+# ----------------------------------------------------------------------------
+def codebook_perplexity(indices, codebook_size: int) -> float:
+    """CodebookPerplexity.update + compute (lightning_module.py:33-51): one-hot counts over all indices,
+    p = counts / total, entropy over the non-zero p, exp."""
+    import numpy as np
+    idx = np.asarray(indices).astype(np.int64).reshape(-1)
+    counts = np.bincount(idx, minlength=codebook_size).astype(np.float64)
+    total = counts.sum()
+    if total == 0:
+        return 0.0
+    p = counts / total
+    p = p[p > 0]
+    return float(np.exp(-(p * np.log(p)).sum()))
+
+
+def codebook_utilization(indices, codebook_size: int) -> float:
+    """CodebookUtilization.update + compute (lightning_module.py:62-69): used-code mask, used / K."""
+    import numpy as np
+    idx = np.asarray(indices).astype(np.int64).reshape(-1)
+    used = np.zeros(codebook_size, dtype=bool)
+    used[idx] = True
+    return float(used.sum() / codebook_size)
+
+
+def calculate_perplexity(counter, codebook_size: int):
+    """inference_full.calculate_perplexity (inference_full.py:570-604): (normalised perplexity, perplexity) from a
+    {index: count} mapping; out-of-range keys count towards the total but carry no probability; 0.0 when empty."""
+    import numpy as np
+    total = sum(counter.values())
+    if total == 0:
+        return 0.0
+    probs = np.zeros(codebook_size)
+    for i, c in counter.items():
+        if i < codebook_size:
+            probs[i] = c / total
+    nz = probs[probs > 0]
+    ent = -np.sum(nz * np.log(nz))
+    return float(np.exp(ent / np.log(codebook_size))), float(np.exp(ent))
+
+
+def index_file_path(output_dir: str, subset: str, fileid: str) -> str:
+    """Where extract_indices.py:534-556 writes an utterance: <out>/<subset>/<speaker>/<chapter>/<fileid>.npy with
+    speaker / chapter = the first two '_'-separated fields of the file id, else the first two '-'-separated
+    fields, else 'unknown'."""
+    import os
+    try:
+        if "_" in fileid:
+            parts = fileid.split("_")
+            speaker, chapter = parts[0], parts[1]
+        elif "-" in fileid:
+            parts = fileid.split("-")
+            speaker, chapter = parts[0], parts[1]
+        else:
+            speaker, chapter = "unknown", "unknown"
+    except IndexError:
+        speaker, chapter = "unknown", "unknown"
+    return os.path.join(output_dir, subset, speaker, chapter, f"{fileid}.npy")
+
+
+def pad_to_stride(waveform: Tensor, stride: int) -> Tensor:
+    """extract_indices.py:134-136: right-pad the last axis with zeros to a multiple of ``stride`` (no-op when aligned)."""
+    t = waveform.shape[-1]
+    if stride and t % stride != 0:
+        waveform = F.pad(waveform, (0, stride - t % stride), mode="constant", value=0)
+    return waveform
