@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from . import _cabi, configs, ops
+from .sharding import shard_range as sharding_range
 from .vq import BigCodecDecoder, BigCodecEncoder, precision_scope
 
 
@@ -113,6 +114,34 @@ class BigCodecModel(nn.Module):
                 del feats
                 outs.append(self._indices_from_features(feat))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def indices_longform(self, x_dev: torch.Tensor, chunk_seconds: float = 60.0, micro_batch: int = 4, group=None,
+                         halo: Optional[int] = None) -> Optional[torch.Tensor]:
+        """One long recording [T] (device, T a multiple of the hop) -> int16 [1, T', n_q] on the device.
+
+        The convolutional front end runs over hop-aligned chunks with a receptive-field halo (batched; dealt out over
+        the ranks of ``group`` when torch.distributed is initialised), the LSTM + final conv + VQ once over the
+        stitched frame-rate features on rank 0 (other ranks return None).  Bit-identical to encoding the recording
+        in one piece (BASELINE.json configs[3])."""
+        from . import longform
+        import torch.distributed as dist
+        x = x_dev.reshape(-1)
+        hop = int(self.encoder.hop_length)
+        if halo is None:
+            halo = longform.halo_frames(self.encoder, antialias_extra=13 if self.cfg["codec_encoder"].get("antialias") else 0)
+        chunk_frames = max(1, int(round(chunk_seconds * 16000)) // hop)
+        plan = longform.plan_chunks(x.numel() // hop, chunk_frames, halo)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        c0, c1 = sharding_range(len(plan), rank, world)
+        with precision_scope(self.precision):
+            parts = longform.chunked_front(self.encoder.front_cl, x, hop, chunk_frames, halo, micro_batch, range(c0, c1))
+            feat = longform.gather_features(parts, len(plan), lambda i: plan[i][1] - plan[i][0], self.encoder.enc_dim,
+                                            x.device, group)
+            if feat is None:
+                return None
+            return self._indices_from_features(feat)
 
     @torch.no_grad()
     def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256) -> np.ndarray:

@@ -95,3 +95,26 @@ def test_inference_full_padding_convention(base_model):
     want = oracle.round_trip(enc_sd, dec_sd, cfg, xp)
     if torch.equal(model(xp.cuda())["indices"].cpu(), want["indices"]):
         assert rel(y, want["x_rec"].squeeze(1)) <= 1e-4
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_longform_chunked_equals_whole_recording(precision):
+    """BASELINE configs[3] (scaled to 40 s): hop-aligned chunks with the receptive-field halo through the front end,
+    one LSTM + VQ pass over the stitched features == the recording encoded in one piece, bit for bit."""
+    from audiotokenization_b200 import configs, longform, synth
+    from audiotokenization_b200.model import BigCodecModel
+    cfg = configs.get_config("base")
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=0)
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision=precision)
+    T = 40 * 16000
+    x = synth.fast_synth_batch(7, 1, T).cuda()
+    whole = model.indices_device(x, micro_batch=1, rnn_batch=1)                    # [1, T', 1] int16
+    chunked = model.indices_longform(x[0, 0], chunk_seconds=9.0, micro_batch=2)     # 5 chunks, the last one short
+    assert chunked.shape == whole.shape and torch.equal(chunked, whole)
+    hop = int(model.encoder.hop_length)
+    halo = longform.halo_frames(model.encoder)
+    from audiotokenization_b200.vq import precision_scope
+    with precision_scope(precision):
+        f_whole = model.encoder.front_cl(x.reshape(1, T, 1))
+        f_chunk = longform.stitch(longform.chunked_front(model.encoder.front_cl, x[0, 0], hop, 1800, halo, 2))
+    assert torch.equal(f_whole, f_chunk)
