@@ -176,7 +176,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world, precision):
@@ -191,7 +191,22 @@ def workload_config(args, world, precision):
             "parallelism": f"utterance-sharded x{world}, no collective on the data path"}
 
 
+def _emit(line: dict) -> None:
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else that libraries print to
+    fd 1 during the run (e.g. NCCL's version banner at communicator creation) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -390,7 +405,7 @@ def main():
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
