@@ -24,6 +24,7 @@ using namespace bc::tc;
 constexpr int LM = 128;         // batch rows per CTA
 constexpr int KC = 128;         // K elements per streamed chunk
 constexpr int GATE_WARPS = 16;
+constexpr int CNT_STRIDE = 16;  // counters per batch tile (>= H / KC)
 constexpr int L_THREADS = (4 + GATE_WARPS) * 32;   // warp 0: TMA, warp 1: MMA, warps 2-3 idle, warps 4-19: gates
 
 struct LstmTcParams {
@@ -32,7 +33,7 @@ struct LstmTcParams {
   const float* skip;       // [B][T][H] or NULL
   float* y;                // [B][T][H]
   __nv_bfloat16* hx;       // [2][m_tiles][split][H/8][128][8]
-  unsigned int* counters;  // [m_tiles]
+  unsigned int* counters;  // [m_tiles][CNT_STRIDE]: one step counter per (batch tile, K chunk of h)
   int B, T, H, NS, nslot, n_slices;
   uint32_t idesc;
   long long* trace;   // debug: [step < 64][8] clock64 stamps of CTA (0,0), steps 100.. (NULL = off)
@@ -102,20 +103,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
     if (lane == 0) {
       uint32_t cc = 0;
       for (int t = 0; t < p.T; ++t) {
-        // wait until every n-slice of this m-tile has published h_{t-1} (step t-1 complete)
-        if (t > 0) {
-          const unsigned int target = (unsigned int)t * (unsigned int)p.n_slices;
-          unsigned int seen;
-          unsigned int spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + m) : "memory");
-            if (++spins > (1u << 26)) __trap();
-          } while (seen < target);
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
-        }
-        LTRACE(0);
+        // K chunk c of h_{t-1} is written by the KC/U n-slices that own its hidden units: each chunk is fetched as soon
+        // as ITS producers have published (per-chunk step counters), so the copies and MMAs of the early chunks overlap
+        // the stragglers of the later ones instead of waiting for the slowest of all n-slices
         const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
         for (int c = 0; c < nchunks; ++c, ++cc) {
+          if (t > 0) {
+            const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
+            unsigned int seen;
+            unsigned int spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + m * CNT_STRIDE + c) : "memory");
+              if (++spins > (1u << 26)) __trap();
+            } while (seen < target);
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
+          }
+          if (c == 0) LTRACE(0);
           const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
           mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
           mbar_expect_tx(bar_full + 8u * slot, slot_bytes);
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
       if (gw == 0 && lane == 0) LTRACE(4);
       asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
       if (gw == 0 && lane == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + m) : "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + m * CNT_STRIDE + (n * U) / KC) : "memory");
         LTRACE(5);
       }
       // off the critical path (overlaps the other CTAs' publishes, the h copies and the next MMA phase):
@@ -290,7 +293,7 @@ struct LstmTcPlan {
 
 bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   if (precision == BC_PREC_FP32) return false;
-  if (H % KC != 0 || H < KC) return false;
+  if (H % KC != 0 || H < KC || H / KC > CNT_STRIDE) return false;
   pl->split = precision == BC_PREC_BF16X3 ? 2 : 1;
   pl->NS = pl->split == 2 ? 32 : 64;
   if ((4 * H) % pl->NS != 0) return false;
@@ -304,7 +307,7 @@ bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   pl->nslot = nslot;
   pl->smem = w + nslot * slot + (2 * nslot + 3) * 8 + 64;
   pl->hx_bytes = (size_t)2 * pl->m_tiles * pl->split * (H / 8) * LM * 8 * 2;
-  pl->ws_bytes = pl->hx_bytes + (size_t)pl->m_tiles * sizeof(unsigned int) + 256;
+  pl->ws_bytes = pl->hx_bytes + (size_t)pl->m_tiles * CNT_STRIDE * sizeof(unsigned int) + 256;
   return true;
 }
 
