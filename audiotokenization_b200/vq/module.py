@@ -26,7 +26,7 @@ LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcge
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
 import os as _os
-STREAM_MIN_CIN = [int(_os.environ.get("BC_STREAM_MIN_CIN", "64"))]    # ... when the layer has at least this many input channels
+STREAM_MIN_CIN = [int(_os.environ.get("BC_STREAM_MIN_CIN", "32"))]    # ... when the layer has at least this many input channels
 STREAM_RU_MIN_C = [int(_os.environ.get("BC_STREAM_RU_MIN_C", "128"))]  # ... ResidualUnits: narrower ones keep their weights resident (ru_persist)
 
 
