@@ -290,22 +290,26 @@ def main():
     torch.cuda.synchronize(dev)
     prof, ops.PROFILE = ops.PROFILE, None
     by_kind, by_layer, by_kernel = {}, {}, {}
+    _pk = load_peaks()
+    RIDGE = _pk["bf16_tflops_sustained"] * 1e12 / (_pk["hbm_gbs"] * 1e9)
     for key, flops, a, b, kernel, nbytes in prof:
         ms = a.elapsed_time(b)
         for table, k in ((by_kind, key[0]), (by_layer, key), (by_kernel, kernel)):
-            d = table.setdefault(k, [0.0, 0.0, 0, 0.0])
+            d = table.setdefault(k, [0.0, 0.0, 0, 0.0, 0.0])
             d[0] += flops
             d[1] += ms
             d[2] += 1
             d[3] += nbytes
+            if nbytes > 0 and flops / nbytes < RIDGE:   # time spent in launches whose own FLOP/byte is below the ridge
+                d[4] += ms
     if args.layer_table and rank == 0:
         with open(args.layer_table, "w") as f:
             f.write("| kind | C_in | C_out | K | stride | dil | T_out | B | prec | launches | ms/step | TFLOP/s |\n"
                     "|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|\n")
-            for k, (fl, ms, n, _) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
+            for k, (fl, ms, n, _, _) in sorted(by_layer.items(), key=lambda kv: -kv[1][1]):
                 f.write("| " + " | ".join(str(v) for v in k) + f" | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} |\n")
             f.write("\n| kernel | launches | ms/step | TFLOP/s | algorithmic GB/s |\n|---|---:|---:|---:|---:|\n")
-            for k, (fl, ms, n, nb) in sorted(by_kernel.items(), key=lambda kv: -kv[1][1]):
+            for k, (fl, ms, n, nb, _) in sorted(by_kernel.items(), key=lambda kv: -kv[1][1]):
                 f.write(f"| `{k}` | {n} | {ms:.2f} | {fl / ms / 1e9 if ms else 0:.1f} | {nb / ms / 1e6 if ms else 0:.0f} |\n")
     CONV_KINDS = ("conv1d", "convtr1d", "resunit")
     conv_flops = sum(v[0] for k, v in by_kind.items() if k in CONV_KINDS)
@@ -315,11 +319,11 @@ def main():
     # dominant kernel = the tcgen05 convolution kernel family with the largest share of the step
     conv_kernels = {k: v for k, v in by_kernel.items() if k in ("conv_stream_kernel", "ru_persist_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel")}
     dom = max(conv_kernels, key=lambda k: conv_kernels[k][1]) if conv_kernels else None
-    d_fl, d_ms, d_n, d_bytes = conv_kernels[dom] if dom else (0.0, 0.0, 0, 0.0)
+    d_fl, d_ms, d_n, d_bytes, d_ms_hbm = conv_kernels[dom] if dom else (0.0, 0.0, 0, 0.0, 0.0)
     # which roof bounds it: arithmetic intensity of its launches against the ridge of the measured peaks
     ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
     intensity = d_fl / d_bytes if d_bytes > 0 else float("inf")
-    hbm_bound = intensity < ridge
+    hbm_bound = d_ms_hbm > 0.5 * d_ms    # the roof under which most of the kernel's time is spent (per-launch FLOP/byte vs ridge)
     tflops = d_fl / (d_ms / 1000.0) / 1e12 if d_ms > 0 else 0.0
     gbs = d_bytes / (d_ms / 1000.0) / 1e9 if d_ms > 0 else 0.0
     traffic = None
@@ -330,10 +334,11 @@ def main():
         traffic = None
 
     def kernel_entry(v):
-        fl, ms, n, nb = v
+        fl, ms, n, nb, ms_hbm = v
         return {"launches": n, "ms_per_step": ms, "tflops": fl / ms / 1e9 if ms else 0.0,
                 "algorithmic_gbs": nb / ms / 1e6 if ms else 0.0, "flop_per_byte": fl / nb if nb else None,
-                "share_of_step": ms / step_ms if step_ms else None}
+                "share_of_step": ms / step_ms if step_ms else None,
+                "time_share_in_hbm_bound_launches": ms_hbm / ms if ms else None}
 
     roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
                 "achieved": gbs if hbm_bound else tflops,
@@ -344,8 +349,9 @@ def main():
                 "peak_source": f"{peaks['source']} ({'copy bandwidth' if hbm_bound else 'bf16 sustained'}, kernel timed inside a long step)",
                 "definition": "dominant kernel = tcgen05 conv kernel family with the largest share of the step; algorithmic bytes "
                               "(fp32 activation read once + written once) or FLOPs (2*MAC, bf16x3 counted once) of its launches in "
-                              "one instrumented step / their CUDA-event time on the launch stream; bound chosen by the launches' "
-                              f"FLOP/byte ({intensity:.0f}) against the ridge of the measured peaks ({ridge:.0f})",
+                              "one instrumented step / their CUDA-event time on the launch stream; bound = the roof under which most of "
+                              f"the kernel's time is spent (each launch's FLOP/byte against the ridge of the measured peaks, {ridge:.0f}; "
+                              f"aggregate {intensity:.0f})",
                 "launches_per_step": d_n, "avg_launch_ms": d_ms / d_n if d_n else None,
                 "algorithmic_bytes_per_launch": d_bytes / d_n if d_n else None,
                 "flop_per_launch": d_fl / d_n if d_n else None, "tflops": tflops,
