@@ -232,6 +232,52 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   }
 }
 
+// stem, sliding-window form: thread = (run of STEM_RUN consecutive steps, 4 output channels).  The K weight quads and the
+// bias stay in registers, the input window slides by one sample per step (one 4-byte load, shared by the lanes of
+// the row), and the G = C_out/4 lanes of a row store one contiguous output row per step -- no per-element index
+// arithmetic, no weight reloads.  G must be a power of two <= 32.
+constexpr int STEM_RUN = 32;
+template <int K>
+__global__ void __launch_bounds__(256) stem_conv_run_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ y, int T_in,
+                                                            int T_out, int C_out, int pad_left, int runs_per_item,
+                                                            long long total_runs) {
+  const int G = C_out >> 2;
+  const int cg = threadIdx.x & (G - 1);
+  const int runs_per_block = 256 / G;
+  float4 wv[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wv[k] = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C_out) + cg);
+  const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long run = (long long)blockIdx.x * runs_per_block + threadIdx.x / G; run < total_runs;
+       run += (long long)gridDim.x * runs_per_block) {
+    const long long b = run / runs_per_item;
+    const int t0 = (int)(run - b * runs_per_item) * STEM_RUN;
+    const float* xb = x + b * T_in;
+    float4* yb = reinterpret_cast<float4*>(y + ((size_t)b * T_out + t0) * C_out) + cg;
+    float win[K];
+#pragma unroll
+    for (int k = 0; k < K - 1; ++k) {
+      const int g = t0 + k - pad_left;
+      win[k] = (g >= 0 && g < T_in) ? __ldg(xb + g) : 0.f;
+    }
+    const int n = min(STEM_RUN, T_out - t0);
+    for (int i = 0; i < n; ++i) {
+      const int g = t0 + i + K - 1 - pad_left;
+      win[K - 1] = (g >= 0 && g < T_in) ? __ldg(xb + g) : 0.f;
+      float4 acc = bv;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        acc.x = fmaf(win[k], wv[k].x, acc.x); acc.y = fmaf(win[k], wv[k].y, acc.y);
+        acc.z = fmaf(win[k], wv[k].z, acc.z); acc.w = fmaf(win[k], wv[k].w, acc.w);
+      }
+      __stcs(yb + (size_t)i * G, acc);
+#pragma unroll
+      for (int k = 0; k < K - 1; ++k) win[k] = win[k + 1];
+    }
+  }
+}
+
 // tail: y[b][t] = act(bias + sum_k sum_ci w[k][ci] * snake?(x[b][t + k - pad_left][ci]))   (C_out == 1, stride 1)
 // CTA = 256 consecutive output steps of one item.  The activated input rows are staged ONCE in shared
 // memory (row stride C_in + 1: conflict-free column walks), then thread t walks its K x C_in window.
@@ -321,6 +367,16 @@ extern "C" int bc_conv1d_fwd(const float* x, const float* w, const float* bias, 
   if (C_in == 1 && stride == 1 && dilation == 1 && C_out % 4 == 0 && !(flags & (BC_CONV_SNAKE_IN | BC_CONV_TANH_OUT)) && !res &&
       y_tstride == 1 && y_toffset == 0 && y_rows == T_out && (K == 7 || K == 3 || K == 1) && bc::aligned16(w) && bc::aligned16(y) &&
       (!bias || bc::aligned16(bias))) {
+    const int G = C_out / 4;
+    if (K == 7 && G <= 32 && (G & (G - 1)) == 0) {   // the codec's stem (k = 7, C_out = 16 / 32 / 64 / 128): sliding-window kernel
+      const int runs_per_item = (T_out + STEM_RUN - 1) / STEM_RUN;
+      const long long total_runs = (long long)B * runs_per_item;
+      const long long want = (total_runs + (256 / G) - 1) / (256 / G);
+      const unsigned blocks = (unsigned)(want < 148ll * 16 ? want : 148ll * 16);
+      stem_conv_run_kernel<7><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, runs_per_item, total_runs);
+      BC_LAUNCH_CHECK("stem_conv_run_kernel");
+      return BC_OK;
+    }
     const long long total = (long long)B * T_out * (C_out / 4);
     const unsigned blocks = (unsigned)((total + 255) / 256 < 148ll * 32 ? (total + 255) / 256 : 148ll * 32);
     if (K == 7) stem_conv_kernel<7><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
