@@ -166,3 +166,39 @@ def test_synthetic_inputs_are_deterministic_and_bounded():
     c = synth.fast_synth_batch(5, 4, 1600)
     assert torch.equal(c, synth.fast_synth_batch(5, 4, 1600)) and c.abs().max() <= 1.0
     assert not torch.equal(c[0], c[1])
+
+
+def test_bench_reference_arm_prints_exactly_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): ONE stdout line, the contract's keys, the CPU
+    oracle port as the implementation; rank > 0 under torchrun prints nothing."""
+    import json
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--cpu-sample-clips", "1", "--clip-seconds", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["e2e"] == {"value": d["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_stream_weight_image_layout():
+    """pack_stream_weight: [n_tile][16-ch group][tap][hi|lo][2 k-planes][N][8] with hi + lo == the fp32 weight to 2^-16."""
+    from audiotokenization_b200 import ops
+    K, cin, cout, N = 3, 64, 512, 256
+    w = torch.randn(K, cin, cout, generator=torch.Generator().manual_seed(5))
+    img = ops.pack_stream_weight(w, N, "bf16x3")
+    assert tuple(img.shape) == (cout // N, cin // 16, K, 2, 2, N, 8) and img.dtype == torch.bfloat16
+    nt, g, k, h, n, e = 1, 2, 1, 1, 77, 5
+    ci, co = g * 16 + h * 8 + e, nt * N + n
+    hi, lo = img[nt, g, k, 0, h, n, e].float(), img[nt, g, k, 1, h, n, e].float()
+    assert hi == w[k, ci, co].to(torch.bfloat16).float()
+    assert abs(float(hi + lo - w[k, ci, co])) <= 2.0 ** -16 * abs(float(w[k, ci, co])) + 1e-12
+    assert tuple(ops.pack_stream_weight(w, N, "bf16").shape) == (cout // N, cin // 16, K, 1, 2, N, 8)
