@@ -415,6 +415,10 @@ int conv1d_tc_fwd(const float* x, const float* w, const float* bias, const float
 }
 
 int ru_persist_slots(int C, int K, int dilation, int precision);
+int ru_group_groups(int C, int K, int dilation, int precision);
+int resunit_group_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
+                      const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T, int C,
+                      int K, int dilation, int pad_left, int precision, cudaStream_t st);
 int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
                         const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
                         int C, int K, int dilation, int pad_left, int precision, cudaStream_t st);
@@ -422,6 +426,8 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
 int resunit_tc_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
                    const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T, int C,
                    int K, int dilation, int pad_left, int precision, cudaStream_t st) {
+  if (ru_persist_slots(C, K, dilation, precision) > 0 && ru_group_groups(C, K, dilation, precision) > 0)
+    return resunit_group_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, st);
   if (ru_persist_slots(C, K, dilation, precision) > 0)
     return resunit_persist_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, st);
   TcParams p;
