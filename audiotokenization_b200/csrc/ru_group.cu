@@ -41,7 +41,7 @@ struct RgParams {
   const float* sa2;
   const float* sib2;
   int B, T, C, K, dil, pad_left;
-  int slab_rows, n_pow2, tiles_per_item, total_tiles, G;
+  int slab_rows, n_pow2, tiles_per_item, total_tiles, G, tmem_cols;
   uint32_t idesc, group_bytes, a_bytes;
 };
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
       bulk_g2s_notx(smem_u32(sW1) + off, reinterpret_cast<const uint8_t*>(p.w1) + off, min(32768u, w1_bytes - off), bar_w);
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * MAX_G * p.n_pow2)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < C; i += RG_THREADS) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * MAX_G * p.n_pow2)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -316,7 +316,7 @@ bool rg_plan(int C, int K, int dilation, int precision, RgPlan* pl) {
   int G = (int)((225 * 1024 - fixed) / group);
   if (G > MAX_G) G = MAX_G;
   const int n_pow2 = C <= 32 ? 32 : 64;
-  if (2 * MAX_G * n_pow2 > 512) return false;
+  if (G > 512 / (2 * n_pow2)) G = 512 / (2 * n_pow2);            // two accumulators per group in 512 TMEM columns
   if (G < 3) return false;                                       // with fewer groups the role pipeline of ru_persist is better
   pl->G = G; pl->split = split; pl->a_bytes = (uint32_t)a; pl->group_bytes = (uint32_t)group;
   pl->smem = fixed + (size_t)G * group;
@@ -352,6 +352,8 @@ int resunit_group_fwd(const float* x, const float* w7, const float* b7, const fl
   if (total > 2147483647ll) return fail(BC_EINVAL, "resunit(group): too many tiles");
   p.total_tiles = (int)total;
   p.G = pl.G;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * pl.G * p.n_pow2) p.tmem_cols <<= 1;   // power of two >= 32
   p.idesc = idesc_bf16_m128(C);
   p.group_bytes = pl.group_bytes;
   p.a_bytes = pl.a_bytes;
