@@ -470,7 +470,8 @@ extern "C" int bc_resunit_plan(int C, int K, int dilation, int precision, int* n
   if (!n_tile || !gpc || !nchunks || !persistent) return bc::fail(BC_EINVAL, "resunit_plan: null output");
   if (precision == BC_PREC_FP32) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: tensor-core modes only");
   if (bc::ru_persist_slots(C, K, dilation, precision) > 0) {
-    *n_tile = C; *gpc = C / 16; *nchunks = 1; *persistent = 1;
+    *n_tile = C; *gpc = C / 16; *nchunks = 1;
+    *persistent = bc::ru_group_groups(C, K, dilation, precision) > 0 ? 2 : 1;   // 2: warpgroup-per-tile kernel, 1: role pipeline
     return BC_OK;
   }
   *persistent = 0;

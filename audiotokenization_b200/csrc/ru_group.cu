@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
     const int pl = gt & (planes - 1);
     const int prow = gt / planes;                                // rows prow + (GT / planes) * j
     constexpr int PRS = GT / planes;
+    constexpr int SB = 6;                                        // 32-byte items a thread keeps in flight while staging
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.sa1 + pl * 8));
     const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.sa1 + pl * 8) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.sib1 + pl * 8));
@@ -137,10 +138,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
       {
         const float* xcol = xb + pl * 8;
         uint8_t* dst = sA + (size_t)pl * plane_bytes;
-        for (int r0 = prow; r0 < p.slab_rows; r0 += PRS * 4) {
-          float4 lo4[4], hi4[4];
+        for (int r0 = prow; r0 < p.slab_rows; r0 += PRS * SB) {   // SB items in flight: the whole slab at C = 32
+          float4 lo4[SB], hi4[SB];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < SB; ++j) {
             const int r = r0 + PRS * j, gr = g0 + r;
             if (r < p.slab_rows && gr >= 0 && gr < p.T) {
               const float4* src = reinterpret_cast<const float4*>(xcol + (size_t)gr * C);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < SB; ++j) {
             const int r = r0 + PRS * j;
             if (r < p.slab_rows) {
               float v[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};

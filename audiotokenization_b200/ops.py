@@ -142,7 +142,7 @@ def resunit(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, 
     flops = 2.0 * B * T * C * C * (k + 1)
     plan = resunit_plan(C, k, dilation, precision)
     with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device,
-                "ru_persist_kernel" if (plan and plan[1]) else "conv1d_tc_kernel", 8.0 * B * T * C):
+                {1: "ru_persist_kernel", 2: "ru_group_kernel"}.get(plan[1] if plan else 0, "conv1d_tc_kernel"), 8.0 * B * T * C):
         check(load_library().bc_resunit_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1), ptr(sa2),
                                             ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left, PRECISIONS[precision],
                                             stream_ptr(x.device)), "bc_resunit_fwd")
@@ -198,7 +198,8 @@ def tc_plan(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision
 
 
 def resunit_plan(c: int, k: int, dilation: int, precision: str):
-    """((n_tile, gpc, nchunks) of the W7 image, persistent?) for the fused ResidualUnit kernel, or None."""
+    """((n_tile, gpc, nchunks) of the W7 image, kernel: 0 per-tile / 1 ru_persist / 2 ru_group) for the fused
+    ResidualUnit kernel, or None."""
     if precision == "fp32":
         return None
     key = ("ru", c, k, dilation, precision)
@@ -207,7 +208,7 @@ def resunit_plan(c: int, k: int, dilation: int, precision: str):
         nt, g, nc, pers = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         rc = load_library().bc_resunit_plan(c, k, dilation, PRECISIONS[precision], ctypes.byref(nt), ctypes.byref(g),
                                             ctypes.byref(nc), ctypes.byref(pers))
-        _TC_PLANS[key] = ((nt.value, g.value, nc.value), bool(pers.value)) if rc == 0 else None
+        _TC_PLANS[key] = ((nt.value, g.value, nc.value), int(pers.value)) if rc == 0 else None
     return _TC_PLANS[key]
 
 

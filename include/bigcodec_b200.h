@@ -115,7 +115,8 @@ int bc_tc_plan(int C_in, int C_out, int K, int stride, int dilation, int precisi
  * bc_conv1d_fwd calls).  pad_left = dilation*(K-1)/2 (or dilation*(K-1) for the causal variant). */
 /* Weight-image geometry bc_resunit_fwd expects for W7 (same meaning as bc_tc_plan; W1 is always
  * n_tile = C, gpc = C/16, nchunks = 1).  *persistent = 1 when the persistent warp-specialised kernel
- * (weights resident in shared memory, C in {16,32,64}) will run, 0 for the per-tile kernel. */
+ * (weights resident in shared memory, C in {16,32,64}) will run, 2 when its warpgroup-per-tile form does
+ * (same weight images; csrc/ru_group.cu), 0 for the per-tile kernel. */
 int bc_resunit_plan(int C, int K, int dilation, int precision, int* n_tile, int* gpc, int* nchunks, int* persistent);
 int bc_resunit_fwd(const float* x, const float* w7, const float* b7, const float* snake1_a, const float* snake1_ib,
                    const float* w1, const float* b1, const float* snake2_a, const float* snake2_ib, float* y,

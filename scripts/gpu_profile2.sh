@@ -15,7 +15,7 @@ timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_
     --log-file gpurun_out/dram_${TAG}.csv $SMALL > gpurun_out/ncu_dram_${TAG}.log 2>&1
 echo "ncu dram exit $?"
 timeout 600 $SMALL > gpurun_out/plain3_${TAG}.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_stream_kernel|ru_persist_kernel" -s 40 -c 4 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_stream_kernel|ru_persist_kernel|ru_group_kernel" -s 40 -c 4 \
     -f -o gpurun_out/prof_${TAG} $SMALL > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out/ | grep ${TAG}
