@@ -31,20 +31,32 @@ constexpr int PROD_WARPS = 8;
 // Warp ids grow with how latency-critical the role is: the SM's warp arbiter favours the higher warp id among
 // eligible warps, and a delayed MMA-issue or weight-copy instruction idles the tensor core, while the
 // activation math of the producers has slack.
-constexpr int MID_WARP0 = 8;
 #ifndef BC_STREAM_MID_WARPS
 #define BC_STREAM_MID_WARPS 8
 #endif
+#ifndef BC_STREAM_PLAIN_PROD
+#define BC_STREAM_PLAIN_PROD 12
+#endif
+#ifndef BC_STREAM_PLAIN_PB
+#define BC_STREAM_PLAIN_PB 6
+#endif
 constexpr int MID_WARPS = BC_STREAM_MID_WARPS;   // 8: two per TMEM lane quarter (one 32-column half each); 4: one per quarter, both halves
 constexpr int MID_HALVES = 8 / MID_WARPS;
-constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;
 constexpr int EPI_WARPS = 4;              // 8 (two per TMEM lane quarter, alternate 32-column blocks) measured slower: the
                                           // register cap of the larger CTA (72) costs every role more than the stores gain
-constexpr int LOAD_WARP = EPI_WARP0 + EPI_WARPS;
-constexpr int MMA_WARP = LOAD_WARP + 1;
-constexpr int S_WARPS = MMA_WARP + 1;
-constexpr int S_THREADS = S_WARPS * 32;
-constexpr int P_BATCH = 6;             // 16-byte loads a producer thread keeps in flight
+// Role layout of one CTA.  The fused ResidualUnit needs the MID stage (22 warps, 80 registers); a plain conv drops
+// it and spends part of the freed register file on more producers and on a larger register cap (18 warps, 96
+// registers: the tile-loop state of every role stays out of local memory).
+template <bool FUSE> struct Roles {
+  static constexpr int PROD = FUSE ? PROD_WARPS : BC_STREAM_PLAIN_PROD;   // multiple of 4 (TMEM lane quarter = warp % 4)
+  static constexpr int MID0 = PROD;
+  static constexpr int MID = FUSE ? MID_WARPS : 0;
+  static constexpr int EPI0 = MID0 + MID;
+  static constexpr int LOAD = EPI0 + EPI_WARPS;
+  static constexpr int MMA = LOAD + 1;
+  static constexpr int THREADS = (MMA + 1) * 32;
+  static constexpr int PB = FUSE ? 6 : BC_STREAM_PLAIN_PB;              // 16-byte loads a producer thread keeps in flight
+};
 constexpr uint32_t A2_PLANE = BM * 16u;  // one 8-channel plane of the re-quantised tile
 constexpr int A2_CH = 64;              // channels per A2 chunk
 constexpr int EPI_LD = 36;               // staging row stride in floats (32 + 4: conflict-free 16-byte accesses both ways)
@@ -121,9 +133,12 @@ struct TilePos {
 #endif
 
 template <int SPLIT, bool FUSE>
-__global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams p) {
+__global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(const SParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  using R = Roles<FUSE>;
+  constexpr int N_PROD = R::PROD, MID_WARP0 = R::MID0, EPI_WARP0 = R::EPI0, LOAD_WARP = R::LOAD, MMA_WARP = R::MMA;
+  constexpr int S_THREADS = R::THREADS, P_BATCH = R::PB;
   const uint32_t plane_bytes = p.plane_bytes;
   const uint32_t a_split = 2u * plane_bytes;
   const uint32_t a2_split = (uint32_t)(A2_CH / 8) * A2_PLANE;
@@ -141,7 +156,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
-      mbar_init(BAR(B_A_FULL + s), PROD_WARPS / p.NA);
+      mbar_init(BAR(B_A_FULL + s), N_PROD / p.NA);
       mbar_init(BAR(B_A_EMPTY + s), 1);
     }
     for (int s = 0; s < 8; ++s) {
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
 
   const bool freerun = (p.dbg_skip & 8) != 0;      // timing experiment: MMA thread free-runs on whatever is in smem
   const bool free_b = (p.dbg_skip & 16) != 0;      // ... only the weight ring is ignored
-  if (warp < PROD_WARPS) {
+  if (warp < N_PROD) {
     if (freerun) goto done;
     // ======================= PRODUCE: activation slabs, one 16-channel group per stage =======================
     // The teams take the groups round-robin, so up to four groups' HBM loads are in flight.  Within a warp 4 lanes cover the 64 contiguous bytes a row holds for this
@@ -193,14 +208,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     // instead of 32 lines, which keeps the L1 wavefront queue out of the critical path.
     // One team per ring slot (NA teams of PROD_WARPS / NA warps): a slot's barriers then see one producer, which
     // is never more than one phase ahead of them.
-    const int team_warps = PROD_WARPS / p.NA;
+    const int team_warps = N_PROD / p.NA;
     const int team = warp / team_warps, tw = warp - team * team_warps;
     if (team >= p.NA) goto done;
     const int rstep = 8 * team_warps;               // rows covered by one load instruction of the team
     const int c4 = lane & 3;                        // which 4 of the group's 16 channels
     const int r_first = tw * 8 + (lane >> 2);       // slab rows r_first + rstep*j
     const bool snake = (p.flags & BC_CONV_SNAKE_IN) != 0;
-    const unsigned inv_stride = 0xFFFFFFFFu / (unsigned)p.stride + 1u;
+    const int ph_first = r_first % p.stride, rr_first = r_first / p.stride;   // once per thread
+    const int rr_step = rstep / p.stride, ph_step = rstep - rr_step * p.stride;
     const uint32_t dst_off = (uint32_t)(c4 >> 1) * plane_bytes + (uint32_t)(c4 & 1) * 8u;
     int it = 0;
     int slot_c = 0, use_c = 0, sq = 0;   // running ring position over ALL stages (every team counts every stage)
@@ -259,39 +275,43 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
               }
             }
           }
-        } else
-        for (int r0 = r_first; r0 < p.slab_rows && !(p.dbg_skip & 1); r0 += rstep * P_BATCH) {
-          float4 v4[P_BATCH];
+        } else {
+          // strided convs and edge tiles: slab row r lives at (phase r % stride, row r / stride); both advance
+          // incrementally from the thread's constant first row
+          const bool inside = g0row >= 0 && g0row + p.slab_rows <= p.T_in;
+          int ph = ph_first, rr = rr_first;
+          for (int r0 = r_first; r0 < p.slab_rows && !(p.dbg_skip & 1); r0 += rstep * P_BATCH) {
+            float4 v4[P_BATCH];
 #pragma unroll
-          for (int j = 0; j < P_BATCH; ++j) {
-            const int r = r0 + rstep * j;
-            const int gr = g0row + r;
-            if (r < p.slab_rows && gr >= 0 && gr < p.T_in) v4[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)gr * p.C_in));
-            else v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (!waited) {   // the loads above are in flight while we wait for the slot
-            long long tw_ = STRACE_ON ? clock64() : 0;
-            mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
-            if (STRACE_ON) wE += clock64() - tw_;
-            waited = true;
-          }
+            for (int j = 0; j < P_BATCH; ++j) {
+              const int r = r0 + rstep * j;
+              const int gr = g0row + r;
+              if (r < p.slab_rows && (inside || (gr >= 0 && gr < p.T_in))) v4[j] = __ldg(reinterpret_cast<const float4*>(xcol + (size_t)gr * p.C_in));
+              else v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (!waited) {   // the loads above are in flight while we wait for the slot
+              long long tw_ = STRACE_ON ? clock64() : 0;
+              mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+              if (STRACE_ON) wE += clock64() - tw_;
+              waited = true;
+            }
 #pragma unroll
-          for (int j = 0; j < P_BATCH; ++j) {
-            const int r = r0 + rstep * j;
-            if (r < p.slab_rows) {
-              float4 v = v4[j];
-              if (snake) {   // snake(0) == 0: padding rows stay zero
-                if (SPLIT == 2) {
-                  v.x = snake_tc(v.x, sa.x, sb.x); v.y = snake_tc(v.y, sa.y, sb.y);
-                  v.z = snake_tc(v.z, sa.z, sb.z); v.w = snake_tc(v.w, sa.w, sb.w);
-                } else {
-                  v.x = snake_bf(v.x, sa.x, sb.x); v.y = snake_bf(v.y, sa.y, sb.y);
-                  v.z = snake_bf(v.z, sa.z, sb.z); v.w = snake_bf(v.w, sa.w, sb.w);
+            for (int j = 0; j < P_BATCH; ++j) {
+              if (r0 + rstep * j < p.slab_rows) {
+                float4 v = v4[j];
+                if (snake) {   // snake(0) == 0: padding rows stay zero
+                  if (SPLIT == 2) {
+                    v.x = snake_tc(v.x, sa.x, sb.x); v.y = snake_tc(v.y, sa.y, sb.y);
+                    v.z = snake_tc(v.z, sa.z, sb.z); v.w = snake_tc(v.w, sa.w, sb.w);
+                  } else {
+                    v.x = snake_bf(v.x, sa.x, sb.x); v.y = snake_bf(v.y, sa.y, sb.y);
+                    v.z = snake_bf(v.z, sa.z, sb.z); v.w = snake_bf(v.w, sa.w, sb.w);
+                  }
                 }
+                store_quad<SPLIT>(v, dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u, a_split);
               }
-              const int rr = p.stride == 1 ? r : (int)__umulhi((unsigned)r, inv_stride);   // exact for r < 2^16
-              const int ph = r - rr * p.stride;
-              store_quad<SPLIT>(v, dst + ((size_t)ph * p.rpp + rr) * 16, a_split);
+              ph += ph_step; rr += rr_step;
+              if (ph >= p.stride) { ph -= p.stride; ++rr; }
             }
           }
         }
@@ -504,12 +524,13 @@ __global__ void __launch_bounds__(S_THREADS, 1) conv_stream_kernel(const SParams
     // The accumulator arrives one row per lane; HBM wants whole lines.  Each warp owns a padded [32 rows][32 + 4]
     // fp32 staging block: the residual is fetched with 8 lanes per row (4 full lines per load instruction), lands in
     // the block, is combined in place by the lane that owns the row, and leaves the same coalesced way.
-    if (warp - EPI_WARP0 >= p.epi_warps) goto done;
+    const int ew = warp - EPI_WARP0;
+    if (ew >= p.epi_warps) goto done;
     const int q = warp & 3;
-    const int cb0 = ((warp - EPI_WARP0) >> 2) * 32, cbstep = (p.epi_warps >> 2) * 32;   // this warp's 32-column blocks
+    const int cb0 = (ew >> 2) * 32, cbstep = (p.epi_warps >> 2) * 32;   // this warp's 32-column blocks
     const bool tanh_out = (p.flags & BC_CONV_TANH_OUT) != 0;
     const float* bias = FUSE ? p.bias2 : p.bias;
-    float* sT = reinterpret_cast<float*>(sStage) + (size_t)(warp - EPI_WARP0) * (32 * EPI_LD);
+    float* sT = reinterpret_cast<float*>(sStage) + (size_t)ew * (32 * EPI_LD);
     const int crow = lane >> 3, cchunk = (lane & 7) * 4;          // coalesced mapping: rows crow + 4*i, 4 floats at cchunk
     int it = 0;
     TilePos tp;
@@ -640,7 +661,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   if ((size_t)pl->plane_bytes * 2 >= (1u << 18)) return false;
   const size_t a2 = fused ? (size_t)2 * (A2_CH / 8) * A2_PLANE * split : 0;
   // eight store warps when the tile has at least two 32-column blocks and shared memory allows, else four
-  int epi_warps = (N >= 64 && EPI_WARPS >= 8) ? 8 : 4;
+  int epi_warps = 4;
   size_t misc = 0;
   const size_t misc0 = N_BARS * 8 + 64 + (32 + MAX_TPU + 2) * 4 + 16 + (fused ? (size_t)4 * N * 4 : 0);
   const size_t budget = 225 * 1024;
@@ -709,7 +730,7 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) 
     if (dev >= 0 && dev < 64) configured[dev][slot] = true;
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, S_THREADS, pl.smem, st>>>(p);
+  kern<<<grid, fused ? Roles<true>::THREADS : Roles<false>::THREADS, pl.smem, st>>>(p);
   BC_LAUNCH_CHECK("conv_stream_kernel");
   return BC_OK;
 }

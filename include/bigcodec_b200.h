@@ -159,7 +159,9 @@ int bc_convtr1d_fwd(const float* x, const float* w_phases, const float* bias,
  *   skip  [B][T][H]   optional, added to the output (ResLSTM's `y + x`, last layer only)
  *   y     [B][T][H]
  *   workspace: bc_lstm_workspace_bytes(B,H) bytes, device, need not be zeroed.
- * Launched as ONE cooperative persistent kernel (grid-wide sync per time step). */
+ * Launched as ONE cooperative persistent kernel (grid-wide sync per time step).  W_hh rows stay resident
+ * in shared memory when every group of 4 hidden units gets its own co-resident CTA (H <= 592 on 148 SMs);
+ * wider layers (H = 1536 of the original BigCodec config) stream them from L2 every step. */
 size_t bc_lstm_workspace_bytes(int B, int H);
 size_t bc_lstm_packed_whh_floats(int H);
 /* host-side helper: w_hh [4H][H] row-major (host ptr) -> packed (host ptr) */

@@ -4,7 +4,7 @@ usage: bench_layer.py [precision] [clips]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from audiotokenization_b200.vq import module as M
+from audiotokenization_b200.vq import module as M, activations
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 clips = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -49,12 +49,13 @@ for c in cases:
         _, ci, co, k, s, T = c
         pad = (s // 2 + s % 2) if s > 1 else (k - 1) // 2
         m = M.WNConv1d(ci, co, kernel_size=k, stride=s, padding=pad).cuda()
+        act = activations.SnakeBeta(ci, alpha_logscale=True).cuda() if s > 1 else None   # EncoderBlock: snake -> strided conv
         xs = [torch.randn(clips, T, ci, device="cuda") for _ in range(3)]
         i = [0]
 
         def fn():
             i[0] = (i[0] + 1) % 3
-            return m.forward_cl(xs[i[0]])
+            return m.forward_cl(xs[i[0]], act=act)
         ms = timeit(fn)
         fl = 2.0 * clips * m.out_length(T) * ci * co * k
         name = f"conv {ci}->{co} k={k} s={s} T_in={T}"

@@ -47,19 +47,24 @@ CASES = [
     ("debug_causal_1s", "debug_causal", False, 15999, 1, "noise"),
     ("debug_nodil_1s", "debug_nodil", False, 16000, 1, "tones"),
     ("config9_base_1s", "config9_base", False, 16000, 1, "tones"),
+    ("default_half_s", "default", False, 8000, 1, "tones"),   # original BigCodec: ngf 48, 1024-d, channels 48..1536
 ]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
+    ap.add_argument("--only", default=None, help="comma-separated case names (default: all)")
     args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else None
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     Enc, Dec = import_reference()
     from audiotokenization_b200 import configs, synth
 
     for name, cfg_name, aa, nsamp, batch, kind in CASES:
+        if only is not None and name not in only:
+            continue
         cfg = configs.get_config(cfg_name, antialias=aa)
         enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=0)
         x = synth.synth_batch(0, batch, nsamp, kind)

@@ -24,7 +24,7 @@ def load_golden(name):
 
 
 GOLDEN_CASES = ["tiny", "tiny_aa", "tiny_ragged", "base_1s", "base_aa_1s", "debug_1s",
-                "debug_causal_1s", "debug_nodil_1s", "config9_base_1s"]
+                "debug_causal_1s", "debug_nodil_1s", "config9_base_1s", "default_half_s"]
 
 
 @pytest.fixture(scope="session")

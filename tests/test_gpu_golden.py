@@ -61,7 +61,7 @@ def test_round_trip_matches_reference_fixture(case):
     print(f"{case}: z rel {e_z32:.2e} (vs f64 {e_z64:.2e}), y rel {e_y:.2e}, idx agree {agree:.4f}")
 
 
-@pytest.mark.parametrize("case", ["base_1s", "debug_1s", "config9_base_1s", "debug_causal_1s", "tiny", "base_aa_1s"])
+@pytest.mark.parametrize("case", ["base_1s", "debug_1s", "config9_base_1s", "debug_causal_1s", "tiny", "base_aa_1s", "default_half_s"])
 def test_tensor_core_split_mode_meets_the_fp32_contract(case):
     """bf16x3 (tcgen05, hi/lo split operands, fused ResidualUnits, tensor-core LSTM): latents and waveforms
     within 1e-3 of the reference (asserted 5x tighter), indices bit-exact where the margin exceeds 1e-5...

@@ -147,8 +147,10 @@ def test_conv_transpose1d_matches_oracle(cin, cout, stride, causal, T):
 
 
 @pytest.mark.parametrize("H,layers,B,T", [(64, 2, 1, 1), (64, 2, 3, 17), (64, 1, 33, 40), (512, 2, 2, 60),
-                                          (128, 2, 70, 9)])
+                                          (128, 2, 70, 9), (768, 1, 3, 12), (1536, 2, 2, 10), (1536, 1, 40, 5)])
 def test_res_lstm_matches_oracle(H, layers, B, T):
+    """H <= 592: W_hh resident in shared memory; H = 768 / 1536 (ngf 48, the original BigCodec config): rows
+    streamed from L2, several unit groups per CTA, cell state in the workspace."""
     g = gen(H + layers + B + T)
     m = M.ResLSTM(H, num_layers=layers)
     sd = {"lstm." + k: v.data.clone() for k, v in m.lstm.named_parameters()}
