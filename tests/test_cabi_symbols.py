@@ -47,7 +47,7 @@ def test_argument_validation_without_touching_the_device():
     assert lib.bc_snake_fwd(None, None, None, None, None, 1, 1, 1, 0, None) == -1
     assert lib.bc_vq_encode(None, None, None, None, None, None, None, 1, 1, 8, 8, None) == -1
     assert lib.bc_lstm_recurrent_fwd(None, None, None, None, None, 1, 1, 32, None) == -1
-    assert lib.bc_lstm_workspace_bytes(3, 64) == 2 * 64 * 32 * 4
+    assert lib.bc_lstm_workspace_bytes(3, 64) == 3 * 64 * 32 * 4   # h (two step parities) + c
     assert lib.bc_lstm_packed_whh_floats(64) == 4 * 64 * 64
 
 
