@@ -37,6 +37,18 @@ constexpr int PROD_WARPS = 8;
 #ifndef BC_STREAM_PLAIN_PROD
 #define BC_STREAM_PLAIN_PROD 12
 #endif
+#ifndef BC_STREAM_REG_CTRL
+#define BC_STREAM_REG_CTRL 48
+#endif
+#ifndef BC_STREAM_REG_PROD_F     // fused kernel: registers per producer / MID thread after the rebalance (launch: 80)
+#define BC_STREAM_REG_PROD_F 80
+#endif
+#ifndef BC_STREAM_REG_MID_F
+#define BC_STREAM_REG_MID_F 80
+#endif
+#ifndef BC_STREAM_REG_PROD_P     // plain conv: registers per producer thread (launch: 96)
+#define BC_STREAM_REG_PROD_P 96
+#endif
 #ifndef BC_STREAM_PLAIN_PB
 #define BC_STREAM_PLAIN_PB 6
 #endif
@@ -54,7 +66,17 @@ template <bool FUSE> struct Roles {
   static constexpr int EPI0 = MID0 + MID;
   static constexpr int LOAD = EPI0 + EPI_WARPS;
   static constexpr int MMA = LOAD + 1;
-  static constexpr int THREADS = (MMA + 1) * 32;
+  static constexpr int WARPS = (MMA + 1 + 3) / 4 * 4;                    // whole warpgroups: setmaxnreg works on groups of 4 warps
+  static constexpr int THREADS = WARPS * 32;
+  // register budget moved between warpgroups after launch: the two control warps (+2 idle) hand most of theirs
+  // to the store warps, whose 32-column accumulator block + residual prefetch do not fit the launch-time cap
+  static constexpr int REG_LAUNCH = FUSE ? 80 : 96;                       // what ptxas picks for THREADS
+  static constexpr int REG_CTRL = BC_STREAM_REG_CTRL;
+  static constexpr int REG_PROD = FUSE ? BC_STREAM_REG_PROD_F : BC_STREAM_REG_PROD_P;
+  static constexpr int REG_MID = BC_STREAM_REG_MID_F;
+  static constexpr int REG_STORE = (WARPS / 4) * REG_LAUNCH - (PROD / 4) * REG_PROD - (MID / 4) * REG_MID - REG_CTRL;
+  static_assert(REG_STORE % 8 == 0 && REG_STORE >= REG_LAUNCH && REG_STORE <= 256, "store warpgroup register budget");
+  static_assert(PROD % 4 == 0 && MID % 4 == 0, "roles must fill whole warpgroups");
   static constexpr int PB = FUSE ? 6 : BC_STREAM_PLAIN_PB;              // 16-byte loads a producer thread keeps in flight
 };
 constexpr uint32_t A2_PLANE = BM * 16u;  // one 8-channel plane of the re-quantised tile
@@ -201,6 +223,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
   const bool freerun = (p.dbg_skip & 8) != 0;      // timing experiment: MMA thread free-runs on whatever is in smem
   const bool free_b = (p.dbg_skip & 16) != 0;      // ... only the weight ring is ignored
   if (warp < N_PROD) {
+    if (R::REG_PROD < R::REG_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_PROD));
     if (freerun) goto done;
     // ======================= PRODUCE: activation slabs, one 16-channel group per stage =======================
     // The teams take the groups round-robin, so up to four groups' HBM loads are in flight.  Within a warp 4 lanes cover the 64 contiguous bytes a row holds for this
@@ -323,7 +346,9 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       }
       if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) p.trace[it * 16 + 12] = wE;
     }
-  } else if (warp == LOAD_WARP) {
+  } else if (warp >= LOAD_WARP) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_CTRL));
+   if (warp == LOAD_WARP) {
     // ======================= WEIGHTS: unit ring, same order as the MMA warp consumes =======================
     if (lane == 0 && !freerun && !free_b) {
       uint32_t slot = 0, phase = 1;   // ring position; `phase` = parity a free slot's empty barrier must have completed
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+   } else if (warp == MMA_WARP) {
     // ======================= MMA issue (warp-uniform control flow, one elected lane issues) =======================
     const uint32_t hi_d = desc_hi(128u);
     const uint32_t uA = smem_u32(sA), uB = smem_u32(sB), uA2 = smem_u32(sA2);
@@ -469,9 +494,12 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         }
       }
     }
+   }
   } else if (warp < EPI_WARP0) {
     // ======================= MID (fused): acc1 -> +b7 -> snake2 -> bf16 A2 chunks =======================
     if (FUSE) {
+      if (R::REG_MID > R::REG_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R::REG_MID));
+      if (R::REG_MID < R::REG_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_MID));
       const int q = warp & 3;
       const int half = (warp - MID_WARP0) >> 2;
       const int row = q * 32 + lane;
@@ -524,6 +552,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     // The accumulator arrives one row per lane; HBM wants whole lines.  Each warp owns a padded [32 rows][32 + 4]
     // fp32 staging block: the residual is fetched with 8 lanes per row (4 full lines per load instruction), lands in
     // the block, is combined in place by the lane that owns the row, and leaves the same coalesced way.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R::REG_STORE));
     const int ew = warp - EPI_WARP0;
     if (ew >= p.epi_warps) goto done;
     const int q = warp & 3;
