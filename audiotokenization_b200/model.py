@@ -24,6 +24,45 @@ def _strip_prefix(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.T
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
+class _FrontPipeline:
+    """Two-stage schedule of the encoder's conv stack over equal-length utterances.
+
+    ``push`` runs the shallow stage on one micro-batch, writing its result straight into a slice of a
+    [deep_batch, T_mid, C_mid] hand-off buffer; whenever the buffer is full (or on ``take``) the deep stage runs
+    over all of it, so that its few tiles per utterance still fill the last round of the persistent kernels."""
+
+    def __init__(self, encoder, deep_batch: int):
+        self.enc, self.cap = encoder, int(deep_batch)
+        self.buf, self.fill, self.feats = None, 0, []
+
+    def push(self, x_cl: torch.Tensor) -> None:
+        b = x_cl.shape[0]
+        if self.cap <= b:                                   # nothing to gather
+            self.feats.append(self.enc.front_cl(x_cl))
+            return
+        if self.fill + b > self.cap:
+            self.flush()
+        if self.buf is None:
+            y = self.enc.front_shallow_cl(x_cl)
+            self.buf = torch.empty((self.cap,) + tuple(y.shape[1:]), device=y.device, dtype=y.dtype)
+            self.buf[:b].copy_(y)
+        else:
+            self.enc.front_shallow_cl(x_cl, out=self.buf[self.fill:self.fill + b])
+        self.fill += b
+
+    def flush(self) -> None:
+        if self.fill:
+            self.feats.append(self.enc.front_deep_cl(self.buf[:self.fill]))
+            self.fill = 0
+
+    def take(self) -> torch.Tensor:
+        """Frame-rate features of everything pushed since the last ``take``, in push order."""
+        self.flush()
+        feat = self.feats[0] if len(self.feats) == 1 else torch.cat(self.feats, dim=0)
+        self.feats = []
+        return feat
+
+
 class BigCodecModel(nn.Module):
     def __init__(self, cfg: dict, enc_state: Optional[dict] = None, dec_state: Optional[dict] = None,
                  device: str = "cuda", precision: str = "fp32"):
@@ -94,25 +133,25 @@ class BigCodecModel(nn.Module):
         return ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
 
     @torch.no_grad()
-    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256) -> torch.Tensor:
+    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256,
+                       deep_batch: int = 64) -> torch.Tensor:
         """Device waveforms [N,1,T] -> int16 [N,T',n_q] on the device.
 
         Two-stage schedule: the convolutional front end runs in micro-batches (bounded activation
         memory: the stem's [mb, T, ngf] tensor is the largest), its frame-rate output (2 KB per frame) is
         collected for up to ``rnn_batch`` utterances, and the sequential LSTM + final conv + VQ then run
-        once over that whole group."""
+        once over that whole group.  Inside the front end the last strided stages run over ``deep_batch``
+        utterances at a time (`_FrontPipeline`)."""
         outs = []
         N = x_dev.shape[0]
         with precision_scope(self.precision):
+            pipe = _FrontPipeline(self.encoder, deep_batch)
             for c0 in range(0, N, rnn_batch):
                 c1 = min(N, c0 + rnn_batch)
-                feats = []
                 for b0 in range(c0, c1, micro_batch):
                     xb = x_dev[b0:min(c1, b0 + micro_batch)]
-                    feats.append(self.encoder.front_cl(xb.reshape(xb.shape[0], xb.shape[2], 1)))
-                feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
-                del feats
-                outs.append(self._indices_from_features(feat))
+                    pipe.push(xb.reshape(xb.shape[0], xb.shape[2], 1))
+                outs.append(self._indices_from_features(pipe.take()))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()
@@ -144,7 +183,8 @@ class BigCodecModel(nn.Module):
             return self._indices_from_features(feat)
 
     @torch.no_grad()
-    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256) -> np.ndarray:
+    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256,
+                        deep_batch: int = 64) -> np.ndarray:
         """Host (ideally pinned) float32 waveforms [N,1,T] -> int16 numpy [N,T',n_q].
 
         Each micro-batch is copied H2D on a side stream while the previous one computes; the int16
@@ -153,9 +193,9 @@ class BigCodecModel(nn.Module):
         if wave_host.is_cuda:
             raise ValueError("extract_indices takes HOST waveforms; use indices_device for device tensors")
         with precision_scope(self.precision):
-            return self._extract_indices(wave_host, micro_batch, rnn_batch)
+            return self._extract_indices(wave_host, micro_batch, rnn_batch, deep_batch)
 
-    def _extract_indices(self, wave_host, micro_batch, rnn_batch):
+    def _extract_indices(self, wave_host, micro_batch, rnn_batch, deep_batch):
         dev = next(self.parameters()).device
         N, _, T = wave_host.shape
         copy_stream = torch.cuda.Stream(device=dev)
@@ -182,19 +222,17 @@ class BigCodecModel(nn.Module):
             spans += [(b0, min(c1, b0 + micro_batch), min(c1, b0 + micro_batch) == c1) for b0 in range(c0, c1, micro_batch)]
         if spans:
             stage(0, spans[0][0], spans[0][1])
-        feats = []
+        pipe = _FrontPipeline(self.encoder, deep_batch)
         for i, (b0, b1, last_of_group) in enumerate(spans):
             k = i % nbuf
             if i + 1 < len(spans):
                 stage(i + 1, spans[i + 1][0], spans[i + 1][1])
             main.wait_event(copied[k])
-            feats.append(self.encoder.front_cl(bufs[k][: b1 - b0]))
+            pipe.push(bufs[k][: b1 - b0])
             consumed[k] = torch.cuda.Event()
             consumed[k].record(main)
             if last_of_group:
-                feat = feats[0] if len(feats) == 1 else torch.cat(feats, dim=0)
-                feats = []
-                i16 = self._indices_from_features(feat)
+                i16 = self._indices_from_features(pipe.take())
                 host = torch.empty(i16.shape, dtype=torch.int16, pin_memory=True)
                 host.copy_(i16, non_blocking=True)
                 results.append(host)

@@ -285,11 +285,17 @@ def conv1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Ten
 
 
 def resunit_stream(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, b1, sa2, sib2, *, k: int,
-                   dilation: int, pad_left: int, precision: str) -> torch.Tensor:
-    """Fused ResidualUnit on the persistent streamed-weight kernel (wide layers)."""
+                   dilation: int, pad_left: int, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused ResidualUnit on the persistent streamed-weight kernel (wide layers).  ``out``: write the result
+    into this contiguous [B,T,C] tensor (e.g. a slice of a larger batch buffer) instead of a fresh one."""
     x = _cl(x)
     B, T, C = x.shape
-    y = torch.empty_like(x)
+    if out is not None:
+        if out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+            raise ValueError("resunit_stream: `out` must be a contiguous float32 tensor of the input's shape on its device")
+        y = out
+    else:
+        y = torch.empty_like(x)
     flops = 2.0 * B * T * C * C * (k + 1)
     with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device, "conv_stream_kernel", 8.0 * B * T * C):
         check(load_library().bc_resunit_stream_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1),

@@ -54,6 +54,32 @@ class BigCodecEncoder(nn.Module):
             h = m.forward_cl(h)
         return h
 
+    # The deep end of the conv stack has few 128-frame tiles per utterance (94 at 256 channels, 19 after the last
+    # strided conv for a 30 s clip): at a micro-batch of 8 that is 5.08 tiles per SM, i.e. a sixth round for 8 % of
+    # the SMs.  So the front end is scheduled in two stages: `front_shallow_cl` on small micro-batches (bounded
+    # activation memory), `front_deep_cl` on several of their outputs at once (full last round).
+    def _front_stages(self):
+        front, _, _, _ = self._split()
+        stem, blocks = front[0], front[1:]
+        k = max(len(blocks) - 2, 0)          # blocks[:k] whole; blocks[k]: units shallow, strided conv deep; the rest deep
+        return stem, blocks[:k], blocks[k], blocks[k + 1:]
+
+    def front_shallow_cl(self, x_cl, out=None):
+        """Stem + EncoderBlocks up to the ResidualUnits of the second-to-last block; ``out`` = destination slice."""
+        stem, whole, pivot, _ = self._front_stages()
+        h = stem.forward_cl(x_cl)
+        for m in whole:
+            h = m.forward_cl(h)
+        return pivot.units_cl(h, out=out)
+
+    def front_deep_cl(self, h):
+        """The pivot block's strided conv + the last block -> frame-rate features."""
+        _, _, pivot, rest = self._front_stages()
+        h = pivot.down_cl(h)
+        for m in rest:
+            h = m.forward_cl(h)
+        return h
+
     def back_cl(self, h):
         """[ResLSTM] + SnakeBeta + final conv on frame-rate features.  The LSTM is sequential in time, so
         it is run over as many utterances at once as possible (its cost per step is almost flat in B)."""

@@ -309,7 +309,7 @@ class ResidualUnit(nn.Module):
             return None
         return conv7, conv1, plan[0], (C, C // 16, 1)
 
-    def _stream_forward(self, x_cl, prec):
+    def _stream_forward(self, x_cl, prec, out=None):
         """Whole unit on the streamed-weight kernel (wide layers), or None."""
         if not FUSE_RESUNIT[0] or self.block[0].antialias:
             return None
@@ -323,13 +323,21 @@ class ResidualUnit(nn.Module):
         sa2, sib2 = self.block[2].act.device_params()
         return ops.resunit_stream(x_cl, conv7.stream_image(prec, nt), conv7.packed()[1], sa1, sib1,
                                   conv1.stream_image(prec, nt), conv1.packed()[1], sa2, sib2, k=conv7.kernel_size,
-                                  dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec)
+                                  dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec, out=out)
 
-    def forward_cl(self, x_cl):
+    def forward_cl(self, x_cl, out=None):
+        """``out``: optional contiguous [B,T,C] destination (a slice of a larger batch buffer)."""
         prec = get_precision()
-        y = self._stream_forward(x_cl, prec)
+        y = self._stream_forward(x_cl, prec, out)
         if y is not None:
             return y
+        y = self._forward_narrow(x_cl, prec)
+        if out is None:
+            return y
+        out.copy_(y)
+        return out
+
+    def _forward_narrow(self, x_cl, prec):
         fused = self._fused_plan(prec)
         if fused is None:
             h = _act_conv(self.block[0], self.block[1], x_cl)
@@ -366,11 +374,20 @@ class EncoderBlock(nn.Module):
                      causal=causal),
         )
 
-    def forward_cl(self, x_cl):
+    def units_cl(self, x_cl, out=None):
+        """The ResidualUnits (time resolution of the block's input); the last one may write into ``out``."""
+        units = list(self.block)[: len(self.block) - 2]
+        for i, ru in enumerate(units):
+            x_cl = ru.forward_cl(x_cl, out=out if i == len(units) - 1 else None)
+        return x_cl
+
+    def down_cl(self, x_cl):
+        """SnakeBeta + strided conv."""
         n = len(self.block)
-        for ru in list(self.block)[: n - 2]:
-            x_cl = ru.forward_cl(x_cl)
         return _act_conv(self.block[n - 2], self.block[n - 1], x_cl)
+
+    def forward_cl(self, x_cl):
+        return self.down_cl(self.units_cl(x_cl))
 
     @torch.no_grad()
     def forward(self, x):

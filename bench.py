@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--clips-per-gpu", type=int, default=512)
     ap.add_argument("--clip-seconds", type=float, default=30.0)
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("BC_MICRO_BATCH", "8")))
+    ap.add_argument("--deep-batch", type=int, default=int(os.environ.get("BC_DEEP_BATCH", "64")),
+                    help="clips per launch of the last strided stages of the conv stack (model._FrontPipeline)")
     ap.add_argument("--rnn-batch", type=int, default=int(os.environ.get("BC_RNN_BATCH", "256")))
     ap.add_argument("--cpu-sample-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -184,7 +186,7 @@ def workload_config(args, world, precision):
                         "across 8xB200 (512 clips per GPU, weak scaling)",
             "model": f"BigCodec {args.model} (cfgs/config11/model/base.yaml)" if args.model == "base" else args.model,
             "clips_per_gpu": args.clips_per_gpu, "clip_seconds": args.clip_seconds, "sample_rate": 16000,
-            "global_clips": args.clips_per_gpu * world, "micro_batch": args.micro_batch, "rnn_batch": args.rnn_batch,
+            "global_clips": args.clips_per_gpu * world, "micro_batch": args.micro_batch, "deep_batch": args.deep_batch, "rnn_batch": args.rnn_batch,
             "precision": precision,
             "weights": "random-init, seed 0 (biases / snake alpha,beta / weight-norm gains randomised)",
             "l2_policy": "inputs_larger_than_l2 (983 MB of waveforms per step; every activation tensor > 126 MB)",
@@ -260,7 +262,7 @@ def main():
     keep = {}
 
     def step_device():
-        keep["idx"] = model.indices_device(x_dev, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch)
+        keep["idx"] = model.indices_device(x_dev, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch, deep_batch=args.deep_batch)
 
     for _ in range(args.warmup):
         step_device()
@@ -275,7 +277,7 @@ def main():
 
     # ---- end to end through the host-buffer API ----------------------------------------------
     def step_e2e():
-        keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch)
+        keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch, deep_batch=args.deep_batch)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()

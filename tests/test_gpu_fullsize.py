@@ -64,6 +64,28 @@ def test_config2_thirty_second_clips_batch_invariance_and_sharding(base_model):
     # determinism
     assert np.array_equal(model.extract_indices(x, micro_batch=6), whole)
     assert len(np.unique(whole)) > 100
+    # the two-stage front-end schedule (deep stages over several micro-batches at once) changes nothing: no
+    # gathering, a hand-off buffer that fills unevenly (2+2 | 2), one that is never full, and the device entry point
+    for mb, deep in ((2, 1), (2, 5), (1, 4), (3, 64)):
+        assert np.array_equal(model.extract_indices(x, micro_batch=mb, deep_batch=deep), whole), (mb, deep)
+    dev = model.indices_device(x.cuda(), micro_batch=2, rnn_batch=4, deep_batch=3).cpu().numpy()
+    assert np.array_equal(dev, whole)
+    f_direct = model.encoder.front_cl(x[:2].cuda().view(2, T, 1))
+    f_staged = model.encoder.front_deep_cl(model.encoder.front_shallow_cl(x[:2].cuda().view(2, T, 1)))
+    assert torch.equal(f_direct, f_staged)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_two_stage_front_schedule_is_bit_identical_on_the_tensor_core_path(base_model, precision):
+    """Tensor-core modes: the last shallow ResidualUnit writes straight into a slice of the hand-off buffer
+    (`out=` of the streamed-weight kernel); gathering must not change a single index."""
+    cfg, enc_sd, dec_sd, _ = base_model
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision=precision)
+    x = synth.fast_synth_batch(0, 5, 160000).pin_memory()
+    plain = model.extract_indices(x, micro_batch=2, deep_batch=1)
+    for mb, deep in ((2, 4), (1, 64), (2, 3)):
+        assert np.array_equal(model.extract_indices(x, micro_batch=mb, deep_batch=deep), plain), (mb, deep)
+    assert np.array_equal(model.indices_device(x.cuda(), micro_batch=2, deep_batch=5).cpu().numpy(), plain)
 
 
 def test_config3_round_trip_batch(base_model):
