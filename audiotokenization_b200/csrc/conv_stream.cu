@@ -38,7 +38,7 @@ constexpr int PROD_WARPS = 8;
 #define BC_STREAM_PLAIN_PROD 12
 #endif
 #ifndef BC_STREAM_REG_CTRL
-#define BC_STREAM_REG_CTRL 48
+#define BC_STREAM_REG_CTRL 56
 #endif
 #ifndef BC_STREAM_REG_PROD_F     // fused kernel: registers per producer / MID thread after the rebalance (launch: 80)
 #define BC_STREAM_REG_PROD_F 80
@@ -48,6 +48,15 @@ constexpr int PROD_WARPS = 8;
 #endif
 #ifndef BC_STREAM_REG_PROD_P     // plain conv: registers per producer thread (launch: 96)
 #define BC_STREAM_REG_PROD_P 96
+#endif
+// Two issue-path experiments, both measured SLOWER in the kernel although they win in the stand-alone issue probe
+// (scripts/probes/mma_probe.cu modes 136/138: the weight ring is only ~2 units deep in time, and releasing a slot
+// one tap later / holding a half-issued unit while waiting for the next one costs more than the hidden latency):
+#ifndef BC_STREAM_DEFER_COMMITS   // 1: a unit's commits are issued behind the first tap of the next unit
+#define BC_STREAM_DEFER_COMMITS 0
+#endif
+#ifndef BC_STREAM_PREFETCH_WAITS  // 1: the next unit's barriers are waited for behind the first tap of the current one
+#define BC_STREAM_PREFETCH_WAITS 0
 #endif
 #ifndef BC_STREAM_PLAIN_PB
 #define BC_STREAM_PLAIN_PB 6
@@ -199,6 +208,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     const int sh = min(tid, p.K - 1) * p.dil;
     s_off[tid] = (uint32_t)(sh % p.stride) * (uint32_t)p.rpp + (uint32_t)(sh / p.stride);
   }
+  if (tid == 0) { s_off[32 + MAX_TPU] = p.idesc; s_off[32 + MAX_TPU + 1] = (uint32_t)p.dil; }
   if (FUSE) {
     for (int i = tid; i < p.N; i += S_THREADS) {
       sPar[i] = __ldg(p.bias + i);
@@ -386,7 +396,13 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       }
     }
    } else if (warp == MMA_WARP) {
-    // ======================= MMA issue (warp-uniform control flow, one elected lane issues) =======================
+    // ======================= MMA issue: one elected lane runs the whole role =======================
+    // The tensor pipe queues only a couple of MMAs, so every instruction between two MMA bursts costs tensor time
+    // (scripts/probes/mma_probe.cu, modes 100+: a satisfied mbarrier try_wait ~55 cycles, a tcgen05.commit ~35-60,
+    // runtime tap guards ~10 per tap; a bare loop reaches the 64-cycle floor at N=128, this nest ~80).  One elected
+    // lane runs the whole role, so nothing re-converges per unit and no descriptor is recomputed per lane.
+    // Optional (off): commits of a unit issued behind the first tap of the next one, next unit's barriers waited for
+    // behind the first tap of the current one (BC_STREAM_DEFER_COMMITS / BC_STREAM_PREFETCH_WAITS).
     const uint32_t hi_d = desc_hi(128u);
     const uint32_t uA = smem_u32(sA), uB = smem_u32(sB), uA2 = smem_u32(sA2);
     const uint32_t b_kplane = (uint32_t)p.N * 16u;       // LBO of the B operand: stride between the two k-planes
@@ -394,106 +410,134 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     const uint32_t tap16 = p.tap_bytes >> 4;
     const uint32_t a_sp = a_split >> 4;
     const int nchunk = p.N / A2_CH;
-    // The tensor pipe buffers only ~4 MMAs, so the issue path must be tight: control flow stays warp-uniform
-    // (descriptor arithmetic lives in uniform registers), ring positions and tap offsets advance incrementally
-    // (nothing divides), and one elected lane issues a whole weight unit as an unrolled block.
-    uint32_t aslot = 0, aph = 0, bslot = 0, bph = 0, a2seq = 0;
+    // Kernel parameters used between two MMAs are read back from shared memory (written in the prologue), so that
+    // they live in registers instead of being re-read from the constant bank inside the issue block
+    const uint32_t idesc = *reinterpret_cast<volatile uint32_t*>(s_off + 32 + MAX_TPU);
+    const uint32_t dil_r = *reinterpret_cast<volatile uint32_t*>(s_off + 32 + MAX_TPU + 1);
     const uint32_t units2 = 4u / (uint32_t)p.gpu1;
     const int last = defer ? n_my : n_my - 1;
-    for (int it = 0; it <= last; ++it) {
-      if (it < n_my) {
-        const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
-        mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(as * p.acc_stride);
-        STRACE(2);
-        for (int g = 0; g < p.groups; ++g) {
-          if (!freerun) mbar_wait(BAR(B_A_FULL + aslot), aph);
+    if (elect_one()) {
+      uint32_t aslot = 0, aph = 0, bslot = 0, bph = 0, a2seq = 0;
+      uint32_t pend_b = 0, pend_a = 0, pend_acc = 0;     // commits owed for the previous unit (barrier addresses, 0 = none)
+      bool a_ready = false, b_ready = false;              // the next slab / weight unit has already been waited for
+      long long units_left = (long long)n_my * p.groups * p.upg + (FUSE ? (long long)n_my * nchunk * units2 : 0);
+#define FLUSH_COMMITS() do { if (pend_b) umma_commit(pend_b); if (pend_a) umma_commit(pend_a); if (pend_acc) umma_commit(pend_acc); \
+                             pend_b = pend_a = pend_acc = 0; } while (0)
+#define PREFETCH_B() do { if (BC_STREAM_PREFETCH_WAITS && --units_left > 0 && !freerun && !free_b) { \
+                            uint32_t nb = bslot + 1, nph = bph; if (nb == (uint32_t)p.NB) { nb = 0; nph ^= 1u; } \
+                            mbar_wait(BAR(B_B_FULL + nb), nph); b_ready = true; } } while (0)
+      for (int it = 0; it <= last; ++it) {
+        if (it < n_my) {
+          const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
+          FLUSH_COMMITS();
+          mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
-          const uint32_t a_lo0 = desc_lo(uA + aslot * p.a_stage, plane_bytes);
-          int k = 0;
-          for (int u = 0; u < p.upg; ++u) {
-            if (!freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
-            tc_fence_after();
-            const int nt = min(p.tpu, p.K - k);
-            uint32_t off[MAX_TPU];
+          const uint32_t d = tmem_base + (uint32_t)(as * p.acc_stride);
+          STRACE(2);
+          for (int g = 0; g < p.groups; ++g) {
+            if (!a_ready && !freerun) mbar_wait(BAR(B_A_FULL + aslot), aph);
+            a_ready = false;
+            const uint32_t a_lo0 = desc_lo(uA + aslot * p.a_stage, plane_bytes);
+            int k = 0;
+            for (int u = 0; u < p.upg; ++u) {
+              if (!b_ready && !freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
+              b_ready = false;
+              const int nt = min(p.tpu, p.K - k);
+              uint32_t off[MAX_TPU];
 #pragma unroll
-            for (int j = 0; j < MAX_TPU; ++j) off[j] = s_off[k + j];
-            const uint32_t b_lo0 = desc_lo(uB + bslot * p.unit_bytes, b_kplane);
-            const uint32_t first_acc = (g | k) ? 1u : 0u;
-            const bool last_u = u == p.upg - 1;
-            if (elect_one()) {
+              for (int j = 0; j < MAX_TPU; ++j)   // un-strided (always, when fused): plain arithmetic, no table look-up
+                off[j] = FUSE ? (uint32_t)(k + j) * dil_r : s_off[k + j];
+              const uint32_t b_lo0 = desc_lo(uB + bslot * p.unit_bytes, b_kplane);
+              const bool last_u = u == p.upg - 1;
 #pragma unroll
               for (int j = 0; j < MAX_TPU; ++j) {
                 if (j < nt) {
                   const uint32_t a_lo = a_lo0 + off[j], b_lo = b_lo0 + (uint32_t)j * tap16;
-                  if (j == 0) mma_bf16_raw_rt(d, a_lo, b_lo, hi_d, hi_d, p.idesc, first_acc);
-                  else        mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
+                  if (j == 0) mma_bf16_raw_rt(d, a_lo, b_lo, hi_d, hi_d, idesc, (g | k) ? 1u : 0u);
+                  else        mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, idesc);
                   if (SPLIT == 2) {
-                    mma_bf16_raw<true>(d, a_lo, b_lo + b_lo_off, hi_d, hi_d, p.idesc);   // a_hi * w_lo
-                    mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);       // a_lo * w_hi
+                    mma_bf16_raw<true>(d, a_lo, b_lo + b_lo_off, hi_d, hi_d, idesc);   // a_hi * w_lo
+                    mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, idesc);       // a_lo * w_hi
+                  }
+                }
+                if (j == 0) {   // housekeeping behind the first tap
+                  FLUSH_COMMITS();
+                  PREFETCH_B();
+                  if (BC_STREAM_PREFETCH_WAITS && last_u && g + 1 < p.groups && !freerun) {
+                    uint32_t na = aslot + 1, nph = aph;
+                    if (na == (uint32_t)p.NA) { na = 0; nph ^= 1u; }
+                    mbar_wait(BAR(B_A_FULL + na), nph);
+                    a_ready = true;
                   }
                 }
               }
-              if (!freerun && !free_b) umma_commit(BAR(B_B_EMPTY + bslot));
+              if (!freerun && !free_b) pend_b = BAR(B_B_EMPTY + bslot);
               if (last_u) {
-                if (!freerun) umma_commit(BAR(B_A_EMPTY + aslot));
-                if (g == p.groups - 1) umma_commit(BAR(B_ACC1_FULL + as));
+                if (!freerun) pend_a = BAR(B_A_EMPTY + aslot);
+                if (g == p.groups - 1) pend_acc = BAR(B_ACC1_FULL + as);
               }
+              if (!BC_STREAM_DEFER_COMMITS) FLUSH_COMMITS();
+              k += nt;
+              if (++bslot == (uint32_t)p.NB) { bslot = 0; bph ^= 1u; }
             }
-            __syncwarp();
-            k += nt;
-            if (++bslot == (uint32_t)p.NB) { bslot = 0; bph ^= 1u; }
+            if (++aslot == (uint32_t)p.NA) { aslot = 0; aph ^= 1u; }
           }
-          if (++aslot == (uint32_t)p.NA) { aslot = 0; aph ^= 1u; }
+          STRACE(3);
         }
-        STRACE(3);
-      }
-      if (FUSE) {
-        const int j = defer ? it - 1 : it;
-        if (j >= 0 && j < n_my) {
-          const int as = p.acc_stages == 2 ? (j & 1) : 0, ause = p.acc_stages == 2 ? (j >> 1) : j;
-          mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
-          tc_fence_after();
-          { const int it = j; STRACE(6); }
-          const uint32_t d2 = tmem_base + (uint32_t)(as * p.acc_stride + p.N);
-          for (int c = 0; c < nchunk; ++c, ++a2seq) {
-            const uint32_t s2 = a2seq & 1u, u2 = a2seq >> 1;
-            mbar_wait(BAR(B_A2_FULL + s2), u2 & 1u);
+        if (FUSE) {
+          const int j = defer ? it - 1 : it;
+          if (j >= 0 && j < n_my) {
+            const int as = p.acc_stages == 2 ? (j & 1) : 0, ause = p.acc_stages == 2 ? (j >> 1) : j;
+            FLUSH_COMMITS();            // MID(j) may be waiting for the accumulator commit that is still owed
+            mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
             tc_fence_after();
-            const uint32_t a_lo0 = desc_lo(uA2 + s2 * a2_chunk, A2_PLANE);
-            for (uint32_t gu = 0; gu < units2; ++gu) {
-              if (!freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
+            { const int it = j; STRACE(6); }
+            const uint32_t d2 = tmem_base + (uint32_t)(as * p.acc_stride + p.N);
+            for (int c = 0; c < nchunk; ++c, ++a2seq) {
+              const uint32_t s2 = a2seq & 1u, u2 = a2seq >> 1;
+              FLUSH_COMMITS();
+              mbar_wait(BAR(B_A2_FULL + s2), u2 & 1u);
               tc_fence_after();
-              const uint32_t b_lo0 = desc_lo(uB + bslot * p.unit_bytes, b_kplane);
-              const uint32_t gc0 = gu * (uint32_t)p.gpu1;
-              if (elect_one()) {
+              const uint32_t a_lo0 = desc_lo(uA2 + s2 * a2_chunk, A2_PLANE);
+              for (uint32_t gu = 0; gu < units2; ++gu) {
+                if (!b_ready && !freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
+                b_ready = false;
+                const uint32_t b_lo0 = desc_lo(uB + bslot * p.unit_bytes, b_kplane);
+                const uint32_t gc0 = gu * (uint32_t)p.gpu1;
 #pragma unroll
                 for (int gg = 0; gg < 4; ++gg) {
                   if (gg < p.gpu1) {
                     const uint32_t gc = gc0 + (uint32_t)gg;
                     const uint32_t a_lo = a_lo0 + gc * ((2u * A2_PLANE) >> 4), b_lo = b_lo0 + (uint32_t)gg * tap16;
-                    mma_bf16_raw_rt(d2, a_lo, b_lo, hi_d, hi_d, p.idesc, ((uint32_t)c | gc) ? 1u : 0u);
+                    mma_bf16_raw_rt(d2, a_lo, b_lo, hi_d, hi_d, idesc, ((uint32_t)c | gc) ? 1u : 0u);
                     if (SPLIT == 2) {
-                      mma_bf16_raw<true>(d2, a_lo, b_lo + b_lo_off, hi_d, hi_d, p.idesc);
-                      mma_bf16_raw<true>(d2, a_lo + (a2_split >> 4), b_lo, hi_d, hi_d, p.idesc);
+                      mma_bf16_raw<true>(d2, a_lo, b_lo + b_lo_off, hi_d, hi_d, idesc);
+                      mma_bf16_raw<true>(d2, a_lo + (a2_split >> 4), b_lo, hi_d, hi_d, idesc);
                     }
                   }
+                  if (gg == 0) {
+                    FLUSH_COMMITS();
+                    PREFETCH_B();
+                  }
                 }
-                if (!freerun && !free_b) umma_commit(BAR(B_B_EMPTY + bslot));
+                if (!freerun && !free_b) pend_b = BAR(B_B_EMPTY + bslot);
                 if (gu == units2 - 1) {
-                  umma_commit(BAR(B_A2_EMPTY + s2));
-                  if (c == nchunk - 1) umma_commit(BAR(B_ACC2_FULL + as));
+                  pend_a = BAR(B_A2_EMPTY + s2);
+                  if (c == nchunk - 1) pend_acc = BAR(B_ACC2_FULL + as);
                 }
+                if (!BC_STREAM_DEFER_COMMITS) FLUSH_COMMITS();
+                if (++bslot == (uint32_t)p.NB) { bslot = 0; bph ^= 1u; }
               }
-              __syncwarp();
-              if (++bslot == (uint32_t)p.NB) { bslot = 0; bph ^= 1u; }
             }
+            { const int it = j; STRACE(7); }
           }
-          { const int it = j; STRACE(7); }
         }
       }
+      FLUSH_COMMITS();
+#undef FLUSH_COMMITS
+#undef PREFETCH_B
     }
+    __syncwarp();
    }
   } else if (warp < EPI_WARP0) {
     // ======================= MID (fused): acc1 -> +b7 -> snake2 -> bf16 A2 chunks =======================

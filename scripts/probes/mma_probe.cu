@@ -10,7 +10,60 @@ using namespace bc::tc;
 // mode 0: all MMAs into one accumulator, same operands; mode 1: alternate two accumulators;
 // mode 2: x3 pattern (a,b) (a,b+lo) (a+lo,b) with tap-shifted A; mode 3: as 2 but other warps hammer smem with stores
 __device__ int g_random = 0;
-__global__ void __launch_bounds__(512, 1) probe(int N, int n_mma, int mode, long long* out, const uint8_t* gsrc) {
+// Bisecting the issue path: the conv_stream loop nest under one elected lane, single pass, with features switched
+// by template flags.  bit0: satisfied mbarrier waits + tcgen05 fences; bit1: commit per unit; bit2: runtime tap
+// count per unit (8-way unrolled block with guards) instead of a fixed 4; bit3: descriptors from ring slots.
+template <int F, bool SPL3>
+__device__ __forceinline__ void issue_nest(uint32_t tmem, uint32_t smem0, uint32_t b_base, uint32_t plane, uint32_t hi_d, uint32_t idesc,
+                                           uint32_t tap16, int N, int ntiles, int4 cfg, int4 cfg2, uint32_t wbar, uint32_t cbar0, uint32_t lo16, uint32_t asp) {
+  const int groups = cfg.x, K = cfg.y, tpu = cfg.z, dil = cfg.w;
+  const int NA = cfg2.x & 63, NB = cfg2.y; const uint32_t a_stage = cfg2.z, unit_bytes = cfg2.w;
+  const int upg = (K + tpu - 1) / tpu;
+  uint32_t aslot = 0, bslot = 0;
+  for (int tile = 0; tile < ntiles; ++tile)
+    for (int g = 0; g < groups; ++g) {
+      if (F & 1) { mbar_wait(wbar, 0); tc_fence_after(); }
+      if (F & 16) mbar_wait(wbar, 0);
+      const uint32_t a_lo_g = desc_lo(smem0 + ((F & 8) ? aslot * a_stage : 0u), plane);
+      int k = 0;
+      for (int u = 0; u < upg; ++u) {
+        if (F & 1) { mbar_wait(wbar, 0); tc_fence_after(); }
+        if (F & 16) mbar_wait(wbar, 0);
+        const int nt = (F & 4) ? min(tpu, K - k) : 4;
+        const uint32_t b_lo_u = desc_lo(b_base + ((F & 8) ? bslot * unit_bytes : 0u), (uint32_t)N * 16u);
+        const uint32_t first_acc = (g | k) ? 1u : 0u;
+        if (F & 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < nt) {
+              const uint32_t a = a_lo_g + (uint32_t)(k + j) * (uint32_t)dil, b = b_lo_u + (uint32_t)j * tap16;
+              if (j == 0) mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, first_acc);
+              else        mma_bf16_raw<true>(tmem, a, b, hi_d, hi_d, idesc);
+              if (SPL3) {
+                mma_bf16_raw<true>(tmem, a, b + lo16, hi_d, hi_d, idesc);
+                mma_bf16_raw<true>(tmem, a + asp, b, hi_d, hi_d, idesc);
+              }
+            }
+            if ((F & 32) && j == 0) { mbar_wait(wbar, 0); if (u == upg - 1) mbar_wait(wbar, 0); }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = a_lo_g + (uint32_t)(k + j) * (uint32_t)dil, b = b_lo_u + (uint32_t)j * tap16;
+            if (j == 0) mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, first_acc);
+            else        mma_bf16_raw<true>(tmem, a, b, hi_d, hi_d, idesc);
+          }
+        }
+        if (F & 2) umma_commit(cbar0 + 8u * (bslot & 3));
+        if (u == upg - 1) umma_commit(cbar0 + 32u + 8u * (aslot & 3));
+        k += nt;
+        if (++bslot == (uint32_t)NB) bslot = 0;
+      }
+      if (++aslot == (uint32_t)NA) aslot = 0;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) probe(int N, int n_mma, int mode, long long* out, const uint8_t* gsrc, int4 cfg, int4 cfg2) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
@@ -40,6 +93,131 @@ __global__ void __launch_bounds__(512, 1) probe(int N, int n_mma, int mode, long
   const uint32_t b_lo0 = desc_lo(b_base, (uint32_t)N * 16u);
   const uint32_t tap16 = ((uint32_t)N * 64u) >> 4, lo16 = ((uint32_t)N * 32u) >> 4;
   const uint32_t hi_d = desc_hi(128u);
+  if (warp == 0 && mode >= 100 && mode < 164) {
+    const int ntiles = n_mma / (cfg.x * 8 * ((cfg2.x & 64) ? 3 : 1));   // 2 units x 4 taps per group in the fixed variant; K=8 tpu=4 keeps both equal
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      const uint32_t s0 = smem_u32(smem), wb = smem_u32(&bars2[8]), cb = smem_u32(&bars2[0]);
+      switch (mode - 100) {
+#define CASE(F) case F: if (cfg2.x & 64) issue_nest<F, true>(tmem, s0, b_base, plane, hi_d, idesc, tap16, N, ntiles, cfg, cfg2, wb, cb, lo16, a_sp); else issue_nest<F, false>(tmem, s0, b_base, plane, hi_d, idesc, tap16, N, ntiles, cfg, cfg2, wb, cb, lo16, a_sp); break;
+        CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(18) CASE(20) CASE(22) CASE(30) CASE(36) CASE(38) CASE(46)
+#undef CASE
+      }
+      t1 = clock64();
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();
+    unsigned m = __ballot_sync(0xffffffffu, t0 != 0);
+    const int src = __ffs(m) - 1;
+    const long long tt0 = __shfl_sync(0xffffffffu, t0, src), tt1 = __shfl_sync(0xffffffffu, t1, src);
+    if (lane == 0 && blockIdx.x == 0) { out[0] = tt1 - tt0; out[1] = t2 - tt0; }
+  } else
+  if (warp == 0 && (mode == 15 || mode == 16)) {
+    // the same loop nest, but ONE elected lane runs all of it (waits included); 15: x3, 16: single pass
+    const int split = mode == 16 ? 1 : 2;
+    const int groups = cfg.x, K = cfg.y, tpu = cfg.z, dil = cfg.w;
+    const int NA = cfg2.x, NB = cfg2.y; const uint32_t a_stage = cfg2.z, unit_bytes = cfg2.w;
+    const int upg = (K + tpu - 1) / tpu;
+    const int ntiles = n_mma / (groups * K * (split == 2 ? 3 : 1));
+    long long t0 = 0, t1 = 0;
+    if (elect_one()) {
+      uint32_t aslot = 0, bslot = 0;
+      t0 = clock64();
+      for (int tile = 0; tile < ntiles; ++tile)
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait(smem_u32(&bars2[8]), 0);      // completed long ago: the cost of a satisfied wait
+          tc_fence_after();
+          const uint32_t a_lo_g = desc_lo(smem_u32(smem) + aslot * a_stage, plane);
+          int k = 0;
+          for (int u = 0; u < upg; ++u) {
+            mbar_wait(smem_u32(&bars2[8]), 0);
+            tc_fence_after();
+            const int nt = min(tpu, K - k);
+            const uint32_t b_lo_u = desc_lo(b_base + bslot * unit_bytes, (uint32_t)N * 16u);
+            const uint32_t first_acc = (g | k) ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nt) {
+                const uint32_t a = a_lo_g + (uint32_t)(k + j) * (uint32_t)dil, b = b_lo_u + (uint32_t)j * tap16;
+                if (j == 0) mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, first_acc);
+                else        mma_bf16_raw<true>(tmem, a, b, hi_d, hi_d, idesc);
+                if (split == 2) {
+                  mma_bf16_raw<true>(tmem, a, b + lo16, hi_d, hi_d, idesc);
+                  mma_bf16_raw<true>(tmem, a + a_sp, b, hi_d, hi_d, idesc);
+                }
+              }
+            }
+            umma_commit(smem_u32(&bars2[bslot & 3]));
+            if (u == upg - 1) umma_commit(smem_u32(&bars2[4 + (aslot & 3)]));
+            k += nt;
+            if (++bslot == (uint32_t)NB) bslot = 0;
+          }
+          if (++aslot == (uint32_t)NA) aslot = 0;
+        }
+      t1 = clock64();
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();
+    unsigned m = __ballot_sync(0xffffffffu, t0 != 0);
+    const int src = __ffs(m) - 1;
+    const long long tt0 = __shfl_sync(0xffffffffu, t0, src), tt1 = __shfl_sync(0xffffffffu, t1, src);
+    if (lane == 0 && blockIdx.x == 0) { out[0] = tt1 - tt0; out[1] = t2 - tt0; }
+  } else
+  if (warp == 0 && mode >= 11 && mode <= 14) {
+    // conv_stream's issue loop: warp-uniform control flow, one elected lane issues an unrolled weight unit
+    // mode 11: x3, 12: single pass, 13: x3 with one commit per group only, 14: x3 fully unrolled switch on nt
+    const int split = mode == 12 ? 1 : 2;
+    const int groups = cfg.x, K = cfg.y, tpu = cfg.z, dil = cfg.w;
+    const int NA = cfg2.x, NB = cfg2.y; const uint32_t a_stage = cfg2.z, unit_bytes = cfg2.w;
+    const int upg = (K + tpu - 1) / tpu;
+    const int ntiles = n_mma / (groups * K * (split == 2 ? 3 : 1));
+    uint32_t aslot = 0, bslot = 0;
+    const long long t0 = clock64();
+    for (int tile = 0; tile < ntiles; ++tile)
+      for (int g = 0; g < groups; ++g) {
+        const uint32_t a_lo_g = desc_lo(smem_u32(smem) + aslot * a_stage, plane);
+        int k = 0;
+        for (int u = 0; u < upg; ++u) {
+          const int nt = min(tpu, K - k);
+          uint32_t off[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) off[j] = (uint32_t)(k + j) * (uint32_t)dil;
+          const uint32_t b_lo_u = desc_lo(b_base + bslot * unit_bytes, (uint32_t)N * 16u);
+          const uint32_t first_acc = (g | k) ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nt) {
+                const uint32_t a = a_lo_g + off[j], b = b_lo_u + (uint32_t)j * tap16;
+                if (j == 0) mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, first_acc);
+                else        mma_bf16_raw<true>(tmem, a, b, hi_d, hi_d, idesc);
+                if (split == 2) {
+                  mma_bf16_raw<true>(tmem, a, b + lo16, hi_d, hi_d, idesc);
+                  mma_bf16_raw<true>(tmem, a + a_sp, b, hi_d, hi_d, idesc);
+                }
+              }
+            }
+            if (mode != 13) umma_commit(smem_u32(&bars2[bslot & 3]));
+            if (u == upg - 1) umma_commit(smem_u32(&bars2[4 + (aslot & 3)]));
+          }
+          __syncwarp();
+          k += nt;
+          if (++bslot == (uint32_t)NB) bslot = 0;
+        }
+        if (++aslot == (uint32_t)NA) aslot = 0;
+      }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t2 = clock64();
+    if (lane == 0 && blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else
   if (warp == 0) {
     long long t0 = 0, t1 = 0, t2 = 0;
     if (elect_one()) {
@@ -48,6 +226,20 @@ __global__ void __launch_bounds__(512, 1) probe(int N, int n_mma, int mode, long
         for (int i = 0; i < n_mma; ++i) mma_bf16_raw_rt(tmem, a_lo0, b_lo0, hi_d, hi_d, idesc, i ? 1u : 0u);
       } else if (mode == 1) {
         for (int i = 0; i < n_mma; ++i) mma_bf16_raw_rt(tmem + (i & 1) * 256, a_lo0, b_lo0, hi_d, hi_d, idesc, i > 1 ? 1u : 0u);
+      } else if (mode == 20) {
+        for (int i = 0; i < n_mma; ++i) {
+          const uint32_t a = a_lo0 + (uint32_t)(i % 7) * 9u, b = b_lo0 + (uint32_t)(i % 7) * tap16;
+          mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, i ? 1u : 0u);
+        }
+      } else if (mode == 21) {
+        uint32_t a = a_lo0, b = b_lo0;
+        for (int i = 0; i < n_mma; i += 4) {   // 4 taps unrolled, descriptors advance by constants
+          mma_bf16_raw_rt(tmem, a, b, hi_d, hi_d, idesc, i ? 1u : 0u);
+          mma_bf16_raw<true>(tmem, a + 9u, b + tap16, hi_d, hi_d, idesc);
+          mma_bf16_raw<true>(tmem, a + 18u, b + 2u * tap16, hi_d, hi_d, idesc);
+          mma_bf16_raw<true>(tmem, a + 27u, b + 3u * tap16, hi_d, hi_d, idesc);
+          a ^= 64u; b ^= 2048u;
+        }
       } else if (mode == 7 || mode == 8) {
         // x3 pattern with a commit after every 2 taps (6 MMAs), like the streamed-weight kernel's unit loop
         for (int i = 0; i < n_mma / 3; ++i) {
@@ -130,23 +322,27 @@ int main() {
   cudaMalloc(&gsrc, 64 << 20);
   cudaMemset(gsrc, 0, 64 << 20);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int Ns[] = {128, 256};
-  for (int rnd : {0, 1})
-  for (int grid : {1, 148})
-  for (int mode : {7})
-    for (int N : Ns)
-      for (int n : {384, 3840}) {
-        cudaMemcpyToSymbol(g_random, &rnd, sizeof(int));
-        printf("random=%d grid=%3d ", rnd, grid);
-        for (int rep = 0; rep < 2; ++rep) {
-          probe<<<grid, 512, 200 * 1024>>>(N, n, mode, out, gsrc);
-          cudaError_t e = cudaDeviceSynchronize();
-          if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-        }
-        long long h[2];
-        cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
-        printf("mode %d N=%3d n_mma=%3d: issue %7lld cyc (%.1f/mma)  complete %7lld cyc (%.1f/mma, floor %d)\n", mode, N, n, h[0],
-               (double)h[0] / n, h[1], (double)h[1] / n, N / 2);
+  struct Case { int mode, N, groups, K, tpu, dil; };
+  Case cases[12];
+  { const int fs[] = {4, 20, 22, 36, 38, 46}; for (int i = 0; i < 6; ++i) { cases[i] = Case{100 + fs[i], 128, 8, 8, 4, 9}; cases[6 + i] = Case{-(100 + fs[i]), 128, 8, 8, 4, 9}; } }
+  for (int grid : {148})
+    for (const Case& c : cases) {
+      const bool x3 = c.mode < 0; const int mode_ = x3 ? -c.mode : c.mode;
+      const int split = x3 ? 3 : (c.mode == 12 || c.mode == 16 || c.mode == 20 || c.mode == 21 || c.mode == 0 || c.mode >= 100) ? 1 : 3;
+      const int n = 26 * c.groups * c.K * split;
+      const int rnd = 1;
+      cudaMemcpyToSymbol(g_random, &rnd, sizeof(int));
+      const int4 cfg = make_int4(c.groups, c.K, c.tpu, c.dil);
+      const int4 cfg2 = make_int4(4 | (x3 ? 64 : 0), 3, 2 * 2 * (182 * 16), c.tpu * c.N * 64);
+      for (int rep = 0; rep < 2; ++rep) {
+        probe<<<grid, 512, 200 * 1024>>>(c.N, n, mode_, out, gsrc, cfg, cfg2);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
+      long long h[2];
+      cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+      printf("grid=%3d mode %2d N=%3d groups=%2d K=%d tpu=%d n_mma=%5d: issue %8lld cyc (%.1f/mma)  complete %8lld cyc (%.1f/mma, floor %d)\n", grid, c.mode,
+             c.N, c.groups, c.K, c.tpu, n, h[0], (double)h[0] / n, h[1], (double)h[1] / n, c.N / 2);
+    }
   return 0;
 }
