@@ -129,8 +129,11 @@ __device__ __forceinline__ void store_quad(const float4& v, uint8_t* d8, uint32_
   *reinterpret_cast<uint2*>(d8) = h;
   if (SPLIT == 2) {
     uint2 l;
-    l.x = pack_bf16x2(v.x - __uint_as_float(h.x << 16), v.y - __uint_as_float(h.x & 0xffff0000u));
-    l.y = pack_bf16x2(v.z - __uint_as_float(h.y << 16), v.w - __uint_as_float(h.y & 0xffff0000u));
+    float r0, r1, r2, r3;
+    unpack2(sub2(pack2(v.x, v.y), bf16x2_as_f32x2(h.x)), r0, r1);
+    unpack2(sub2(pack2(v.z, v.w), bf16x2_as_f32x2(h.y)), r2, r3);
+    l.x = pack_bf16x2(r0, r1);
+    l.y = pack_bf16x2(r2, r3);
     *reinterpret_cast<uint2*>(d8 + lo_offset) = l;
   }
 }
@@ -296,13 +299,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
               if (r0 + rstep * j < p.slab_rows) {
                 float4 v = v4[j];
                 if (snake) {
-                  if (SPLIT == 2) {
-                    v.x = snake_tc(v.x, sa.x, sb.x); v.y = snake_tc(v.y, sa.y, sb.y);
-                    v.z = snake_tc(v.z, sa.z, sb.z); v.w = snake_tc(v.w, sa.w, sb.w);
-                  } else {
-                    v.x = snake_bf(v.x, sa.x, sb.x); v.y = snake_bf(v.y, sa.y, sb.y);
-                    v.z = snake_bf(v.z, sa.z, sb.z); v.w = snake_bf(v.w, sa.w, sb.w);
-                  }
+                  snake4<SPLIT>(v, sa, sb);
                 }
                 store_quad<SPLIT>(v, d8 + j * dstep, a_split);
               }
@@ -333,13 +330,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
               if (r0 + rstep * j < p.slab_rows) {
                 float4 v = v4[j];
                 if (snake) {   // snake(0) == 0: padding rows stay zero
-                  if (SPLIT == 2) {
-                    v.x = snake_tc(v.x, sa.x, sb.x); v.y = snake_tc(v.y, sa.y, sb.y);
-                    v.z = snake_tc(v.z, sa.z, sb.z); v.w = snake_tc(v.w, sa.w, sb.w);
-                  } else {
-                    v.x = snake_bf(v.x, sa.x, sb.x); v.y = snake_bf(v.y, sa.y, sb.y);
-                    v.z = snake_bf(v.z, sa.z, sb.z); v.w = snake_bf(v.w, sa.w, sb.w);
-                  }
+                  snake4<SPLIT>(v, sa, sb);
                 }
                 store_quad<SPLIT>(v, dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u, a_split);
               }

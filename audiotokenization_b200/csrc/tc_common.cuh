@@ -132,6 +132,39 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2, sm_100): one issue slot for two IEEE-identical fp32 operations.
+// The activation math of these kernels is bound by instruction issue, not by the FMA pipe, so pairing halves its cost.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// bf16 hi halves of two floats as the two fp32 values they represent
+__device__ __forceinline__ f32x2 bf16x2_as_f32x2(uint32_t h) { return pack2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)); }
+
 template <int SPLIT>
 __device__ __forceinline__ void split_store(const float v[8], uint8_t* dst, uint32_t lo_offset) {
   uint4 h;
@@ -139,13 +172,15 @@ __device__ __forceinline__ void split_store(const float v[8], uint8_t* dst, uint
   h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(dst) = h;
   if (SPLIT == 2) {
-    float r[8];
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+    uint32_t ll[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) r[e] = v[e] - __bfloat162float(__float2bfloat16_rn(v[e]));
-    uint4 l;
-    l.x = pack_bf16x2(r[0], r[1]); l.y = pack_bf16x2(r[2], r[3]);
-    l.z = pack_bf16x2(r[4], r[5]); l.w = pack_bf16x2(r[6], r[7]);
-    *reinterpret_cast<uint4*>(dst + lo_offset) = l;
+    for (int e = 0; e < 4; ++e) {
+      float r0, r1;
+      unpack2(sub2(pack2(v[2 * e], v[2 * e + 1]), bf16x2_as_f32x2(hh[e])), r0, r1);   // exact: v - bf16(v)
+      ll[e] = pack_bf16x2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(dst + lo_offset) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
   }
 }
 
@@ -161,26 +196,51 @@ __device__ __forceinline__ float snake_tc(float x, float a, float ib) {
   return fmaf(ib, s * s, x);
 }
 
+// the same arithmetic, operation for operation, on two elements per instruction (bit-identical results)
+__device__ __forceinline__ f32x2 snake_tc2(f32x2 x, f32x2 a, f32x2 ib) {
+  const f32x2 t = mul2(x, a);
+  f32x2 n = fma2(t, pack2(0.318309886183790672f, 0.318309886183790672f), pack2(12582912.f, 12582912.f));
+  n = add2(n, pack2(-12582912.f, -12582912.f));
+  f32x2 r = fma2(n, pack2(-3.14159274101257324f, -3.14159274101257324f), t);
+  r = fma2(n, pack2(8.74227765734758577e-8f, 8.74227765734758577e-8f), r);
+  float r0, r1;
+  unpack2(r, r0, r1);
+  const f32x2 s = pack2(__sinf(r0), __sinf(r1));
+  return fma2(ib, mul2(s, s), x);
+}
+
 // single-pass bf16 mode: the operand is rounded to 8 mantissa bits right after, so the SFU sine on the raw
 // product is plenty (its error grows like |x*a| * 6e-8, three orders below the bf16 rounding).
 __device__ __forceinline__ float snake_bf(float x, float a, float ib) {
   const float s = __sinf(x * a);
   return fmaf(ib, s * s, x);
 }
+__device__ __forceinline__ f32x2 snake_bf2(f32x2 x, f32x2 a, f32x2 ib) {
+  float t0, t1;
+  unpack2(mul2(x, a), t0, t1);
+  const f32x2 s = pack2(__sinf(t0), __sinf(t1));
+  return fma2(ib, mul2(s, s), x);
+}
 
 template <int SPLIT>
 __device__ __forceinline__ void snake8(float v[8], const float4& a0, const float4& a1, const float4& b0, const float4& b1) {
-  if (SPLIT == 2) {
-    v[0] = snake_tc(v[0], a0.x, b0.x); v[1] = snake_tc(v[1], a0.y, b0.y);
-    v[2] = snake_tc(v[2], a0.z, b0.z); v[3] = snake_tc(v[3], a0.w, b0.w);
-    v[4] = snake_tc(v[4], a1.x, b1.x); v[5] = snake_tc(v[5], a1.y, b1.y);
-    v[6] = snake_tc(v[6], a1.z, b1.z); v[7] = snake_tc(v[7], a1.w, b1.w);
-  } else {
-    v[0] = snake_bf(v[0], a0.x, b0.x); v[1] = snake_bf(v[1], a0.y, b0.y);
-    v[2] = snake_bf(v[2], a0.z, b0.z); v[3] = snake_bf(v[3], a0.w, b0.w);
-    v[4] = snake_bf(v[4], a1.x, b1.x); v[5] = snake_bf(v[5], a1.y, b1.y);
-    v[6] = snake_bf(v[6], a1.z, b1.z); v[7] = snake_bf(v[7], a1.w, b1.w);
+  const f32x2 aa[4] = {pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w)};
+  const f32x2 bb[4] = {pack2(b0.x, b0.y), pack2(b0.z, b0.w), pack2(b1.x, b1.y), pack2(b1.z, b1.w)};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const f32x2 x = pack2(v[2 * e], v[2 * e + 1]);
+    const f32x2 y = SPLIT == 2 ? snake_tc2(x, aa[e], bb[e]) : snake_bf2(x, aa[e], bb[e]);
+    unpack2(y, v[2 * e], v[2 * e + 1]);
   }
+}
+
+// four elements (one 16-byte load): the producers of the streamed-weight kernel
+template <int SPLIT>
+__device__ __forceinline__ void snake4(float4& v, const float4& a, const float4& b) {
+  const f32x2 y0 = SPLIT == 2 ? snake_tc2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y)) : snake_bf2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y));
+  const f32x2 y1 = SPLIT == 2 ? snake_tc2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w)) : snake_bf2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w));
+  unpack2(y0, v.x, v.y);
+  unpack2(y1, v.z, v.w);
 }
 
 // 32 accumulator columns of this thread's TMEM lane in one instruction
