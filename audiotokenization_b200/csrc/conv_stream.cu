@@ -567,10 +567,8 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
               const float4 bi0 = *reinterpret_cast<const float4*>(sPar + ch), bi1 = *reinterpret_cast<const float4*>(sPar + ch + 4);
               const float4 s0 = *reinterpret_cast<const float4*>(sPar + p.N + ch), s1 = *reinterpret_cast<const float4*>(sPar + p.N + ch + 4);
               const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch), i1 = *reinterpret_cast<const float4*>(sPar + 2 * p.N + ch + 4);
-              float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
-                            __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
-                            __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
-                            __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+              float v[8];
+            acc_bias8(r + 8 * j, bi0, bi1, v);
               snake8<SPLIT>(v, s0, s1, i0, i1);
               split_store<SPLIT>(v, dst + (size_t)j * A2_PLANE, a2_split);
             }
@@ -648,14 +646,14 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
                                  __uint_as_float(r[4 * j + 3]));
           if (FUSE) {
             const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * p.N + c0 + 4 * j);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            v = add4(v, bb);
           } else if (bp) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(bp + c0) + j);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            v = add4(v, bb);
           }
           if (rp) {
             const float4 t4 = *reinterpret_cast<const float4*>(own + 4 * j);
-            v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+            v = add4(v, t4);
           }
           if (tanh_out) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
           *reinterpret_cast<float4*>(own + 4 * j) = v;

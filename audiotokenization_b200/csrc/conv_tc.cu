@@ -217,10 +217,8 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
           const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.sa2 + c) + 1);
           const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.sib2 + c));
           const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.sib2 + c) + 1);
-          float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
-                        __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
-                        __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
-                        __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+          float v[8];
+            acc_bias8(r + 8 * j, bi0, bi1, v);
           snake8<SPLIT>(v, s0, s1, i0, i1);
           split_store<SPLIT>(v, sA2 + (size_t)(c / 8) * a2_plane + (size_t)(q * 32 + lane) * 16, a2_split);
         }
@@ -283,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, TC_MIN_CTAS) conv1d_tc_kernel(cons
                                    __uint_as_float(r[4 * j + 3]));
             if (bias) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + co_base + c0) + j);
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              v = add4(v, bb);
             }
             if (rp) { v.x += res4[j].x; v.y += res4[j].y; v.z += res4[j].z; v.w += res4[j].w; }
             if (tanh_out) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }

@@ -214,10 +214,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
             const float4 bi0 = *reinterpret_cast<const float4*>(sPar + c), bi1 = *reinterpret_cast<const float4*>(sPar + c + 4);
             const float4 s0 = *reinterpret_cast<const float4*>(sPar + C + c), s1 = *reinterpret_cast<const float4*>(sPar + C + c + 4);
             const float4 i0 = *reinterpret_cast<const float4*>(sPar + 2 * C + c), i1 = *reinterpret_cast<const float4*>(sPar + 2 * C + c + 4);
-            float v[8] = {__uint_as_float(r[8 * j + 0]) + bi0.x, __uint_as_float(r[8 * j + 1]) + bi0.y,
-                          __uint_as_float(r[8 * j + 2]) + bi0.z, __uint_as_float(r[8 * j + 3]) + bi0.w,
-                          __uint_as_float(r[8 * j + 4]) + bi1.x, __uint_as_float(r[8 * j + 5]) + bi1.y,
-                          __uint_as_float(r[8 * j + 6]) + bi1.z, __uint_as_float(r[8 * j + 7]) + bi1.w};
+            float v[8];
+            acc_bias8(r + 8 * j, bi0, bi1, v);
             snake8<SPLIT>(v, s0, s1, i0, i1);
             split_store<SPLIT>(v, dst + (size_t)(c / 8) * a2_plane, a2_split);
           }
@@ -268,10 +266,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           for (int j = 0; j < 8; ++j) {
             const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * C + c0 + 4 * j);
             float4 t4 = *reinterpret_cast<const float4*>(own + c0 + 4 * j);
-            t4.x += __uint_as_float(r[4 * j + 0]) + bb.x;
-            t4.y += __uint_as_float(r[4 * j + 1]) + bb.y;
-            t4.z += __uint_as_float(r[4 * j + 2]) + bb.z;
-            t4.w += __uint_as_float(r[4 * j + 3]) + bb.w;
+            t4 = add4(t4, acc_bias4(r + 4 * j, bb));
             *reinterpret_cast<float4*>(own + c0 + 4 * j) = t4;
           }
         }

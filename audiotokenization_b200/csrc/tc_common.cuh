@@ -234,6 +234,27 @@ __device__ __forceinline__ void snake8(float v[8], const float4& a0, const float
   }
 }
 
+// accumulator words r[0..7] + bias -> v[0..7], two elements per instruction
+__device__ __forceinline__ void acc_bias8(const uint32_t* r, const float4& b0, const float4& b1, float v[8]) {
+  unpack2(add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b0.x, b0.y)), v[0], v[1]);
+  unpack2(add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b0.z, b0.w)), v[2], v[3]);
+  unpack2(add2(pack2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack2(b1.x, b1.y)), v[4], v[5]);
+  unpack2(add2(pack2(__uint_as_float(r[6]), __uint_as_float(r[7])), pack2(b1.z, b1.w)), v[6], v[7]);
+}
+// (r[0..3] + b) as a float4
+__device__ __forceinline__ float4 acc_bias4(const uint32_t* r, const float4& b) {
+  float4 v;
+  unpack2(add2(pack2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack2(b.x, b.y)), v.x, v.y);
+  unpack2(add2(pack2(__uint_as_float(r[2]), __uint_as_float(r[3])), pack2(b.z, b.w)), v.z, v.w);
+  return v;
+}
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
+  float4 v;
+  unpack2(add2(pack2(a.x, a.y), pack2(b.x, b.y)), v.x, v.y);
+  unpack2(add2(pack2(a.z, a.w), pack2(b.z, b.w)), v.z, v.w);
+  return v;
+}
+
 // four elements (one 16-byte load): the producers of the streamed-weight kernel
 template <int SPLIT>
 __device__ __forceinline__ void snake4(float4& v, const float4& a, const float4& b) {
