@@ -245,17 +245,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
       // ---- store: acc2 + b1 + x -> y ----
       mbar_wait(bar1, ph);          // also: the 1x1 conv has finished reading A2, the K-tap conv the slab -> staging is free
       tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < NRES; ++i) *reinterpret_cast<float4*>(sT + (size_t)(crow + RPI * i) * SLD + cchunk) = res4[i];
-      if (NRES * RPI < BM) {         // rows beyond the register prefetch (C = 64: second half of the tile)
-        const float* rp = xb + (size_t)(t0 + crow) * C + cchunk;
-#pragma unroll
-        for (int i = NRES; i < BM / RPI; ++i) {
-          const float4 v = (t0 + crow + RPI * i < p.T) ? __ldg(reinterpret_cast<const float4*>(rp + (size_t)RPI * i * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(sT + (size_t)(crow + RPI * i) * SLD + cchunk) = v;
-        }
-      }
-      group_sync(g);
+      // The residual never goes through the staging block: it was fetched in the coalesced (row group, 16-byte
+      // chunk) mapping, which is also the mapping of the final store, so it is added there, from registers.
       {
         float* own = sT + (size_t)row * SLD;
 #pragma unroll
@@ -265,9 +256,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * C + c0 + 4 * j);
-            float4 t4 = *reinterpret_cast<const float4*>(own + c0 + 4 * j);
-            t4 = add4(t4, acc_bias4(r + 4 * j, bb));
-            *reinterpret_cast<float4*>(own + c0 + 4 * j) = t4;
+            *reinterpret_cast<float4*>(own + c0 + 4 * j) = acc_bias4(r + 4 * j, bb);
           }
         }
       }
@@ -275,10 +264,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
       group_sync(g);
       {
         float* yp = p.y + ((size_t)b * p.T + t0 + crow) * C + cchunk;
+        const float* rp = xb + (size_t)(t0 + crow) * C + cchunk;
 #pragma unroll
         for (int i = 0; i < BM / RPI; ++i) {
           const float4 v = *reinterpret_cast<const float4*>(sT + (size_t)(crow + RPI * i) * SLD + cchunk);
-          if (t0 + crow + RPI * i < p.T) __stcs(reinterpret_cast<float4*>(yp + (size_t)RPI * i * C), v);
+          if (t0 + crow + RPI * i < p.T) {
+            const float4 xr = i < NRES ? res4[i] : __ldg(reinterpret_cast<const float4*>(rp + (size_t)RPI * i * C));   // rows beyond the register prefetch
+            __stcs(reinterpret_cast<float4*>(yp + (size_t)RPI * i * C), add4(xr, v));
+          }
         }
       }
       group_sync(g);               // staging reads done before the next tile's slab overwrites it
