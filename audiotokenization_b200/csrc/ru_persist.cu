@@ -40,6 +40,8 @@ constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;    // 4 warps
 constexpr int RU_WARPS = EPI_WARP0 + 4;
 constexpr int RU_THREADS = RU_WARPS * 32;
 constexpr int LD_BATCH = 5;
+constexpr int EPI_LD = 36;                           // staging row stride in floats (32 + 4: conflict-free 16-byte accesses both ways)
+constexpr size_t STAGE_BYTES = (size_t)4 * 32 * EPI_LD * sizeof(float);   // one [32 rows][32 + 4] block per store warp
 
 struct RuParams {
   const float* x;
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
   uint8_t* sA = sW1 + w1_split * SPLIT;
   uint8_t* sA2 = sA + (size_t)a_slot * p.nslot;
   float* sPar = reinterpret_cast<float*>(sA2 + (size_t)a2_slot * p.nslot);  // b7 | sa2 | sib2 | b1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 4 * C);
+  float* sStage = sPar + 4 * C;                      // 4 x [32][EPI_LD] fp32: transposes accumulator rows into whole HBM lines
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 4 * 32 * EPI_LD);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
   const uint32_t bar0 = smem_u32(bars);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
@@ -317,27 +320,33 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     }
   } else {
     // ======================= STORE: acc2 + b1 + x -> y =======================
+    // The accumulator arrives one row per lane; a lane-per-row global access costs 32 L1 wavefronts per instruction
+    // (the L1 data pipe was 92 % busy and the bound of this kernel).  Each warp owns a padded [32 rows][32 + 4] fp32
+    // block: bias-added rows go in, and leave with 8 lanes per row (4 whole lines per instruction); the residual is
+    // fetched in that same coalesced mapping and added from registers on the way out.
     const int q = warp & 3;
+    float* sT = sStage + (size_t)(warp - EPI_WARP0) * (32 * EPI_LD);
+    const int crow = lane >> 3, cchunk = (lane & 7) * 4;     // coalesced mapping: rows crow + 4*i, 4 floats at cchunk
     int it = 0;
     int b = first / p.tiles_per_item, tt = first - b * p.tiles_per_item;
     for (int tile = first; tile < p.total_tiles; tile += step, ++it, tt += step) {
       while (tt >= p.tiles_per_item) { tt -= p.tiles_per_item; ++b; }
       const int as = it & 1, ause = it >> 1;
-      const int t = tt * BM + q * 32 + lane;
-      const bool row_ok = t < p.T;
-      const size_t off = ((size_t)b * p.T + (row_ok ? t : 0)) * C;
-      const float* rp = p.x + off;
-      float* yp = p.y + off;
+      const int trow0 = tt * BM + q * 32;                    // first row of this warp's block
+      const size_t off0 = ((size_t)b * p.T + trow0 + crow) * C + cchunk;
+      const float* rp = p.x + off0;
+      float* yp = p.y + off0;
+      const size_t istep = (size_t)4 * C;
+      const int rows_ok = p.T - trow0 - crow;                // row 4*i of this lane is valid iff 4*i < rows_ok
       const uint32_t taddr = tmem_base + (uint32_t)((2 + as) * p.n_pow2) + ((uint32_t)(q * 32) << 16);
       if (warp == EPI_WARP0) TRACE(9);
       for (int c0 = 0; c0 < C; c0 += 32) {
-        const int n8 = min(4, (C - c0) / 8);
+        const int ncol = min(32, C - c0), n8 = ncol / 8;
+        const bool col_ok = cchunk < ncol;
         float4 res4[8];
-        if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < 2 * n8) res4[j] = __ldg(reinterpret_cast<const float4*>(rp + c0) + j);
-        }
+        for (int i = 0; i < 8; ++i)
+          res4[i] = (col_ok && 4 * i < rows_ok) ? __ldg(reinterpret_cast<const float4*>(rp + c0 + i * istep)) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (c0 == 0) {
           mbar_wait(BAR(B_ACC2_FULL + as), (uint32_t)(ause & 1));
           tc_fence_after();
@@ -350,17 +359,23 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACC2_EMPTY + as));
         }
-        if (row_ok) {
+        float* own = sT + lane * EPI_LD;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < 2 * n8) {
-              const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * C + c0 + 4 * j);
-              float4 v;
-              v = add4(acc_bias4(r + 4 * j, bb), res4[j]);
-              __stcs(reinterpret_cast<float4*>(yp + c0) + j, v);
-            }
+        for (int j = 0; j < 8; ++j) {
+          if (j < 2 * n8) {
+            const float4 bb = *reinterpret_cast<const float4*>(sPar + 3 * C + c0 + 4 * j);
+            *reinterpret_cast<float4*>(own + 4 * j) = acc_bias4(r + 4 * j, bb);
           }
         }
+        __syncwarp();
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(sT + (4 * i + crow) * EPI_LD + cchunk);
+            if (4 * i < rows_ok) __stcs(reinterpret_cast<float4*>(yp + c0 + i * istep), add4(v, res4[i]));
+          }
+        }
+        __syncwarp();
       }
       if (warp == EPI_WARP0) TRACE(11);
     }
@@ -379,7 +394,7 @@ size_t ru_smem_bytes(int C, int K, int dil, int split, int nslot) {
   const size_t w = (size_t)split * ((size_t)K * C * C * 2 + (size_t)C * C * 2);
   const size_t a_slot = ((size_t)split * (C / 8) * slab_rows * 16 + 127) & ~size_t(127);
   const size_t a2_slot = (size_t)split * (C / 8) * BM * 16;
-  return w + nslot * (a_slot + a2_slot) + 4 * C * sizeof(float) + N_BARS * 8 + 64;
+  return w + nslot * (a_slot + a2_slot) + 4 * C * sizeof(float) + STAGE_BYTES + N_BARS * 8 + 64;
 }
 
 }  // namespace
