@@ -74,6 +74,14 @@ struct RuParams {
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
        B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
 
+// Stride between the 8-channel planes of the activation slab: rows * 16 B, padded to 16 (mod 128) so that the up to 8
+// planes a warp writes side by side (one 16-byte row chunk each) fall into different banks.
+__host__ __device__ inline uint32_t ru_plane_bytes(int slab_rows) {
+  uint32_t b = (uint32_t)slab_rows * 16u;
+  while (b % 128u != 16u) b += 16u;
+  return b;
+}
+
 template <int SPLIT, int GROUPS>
 __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
   const int planes = C / 8;
   const uint32_t w7_split = (uint32_t)p.K * C * C * 2u;
   const uint32_t w1_split = (uint32_t)C * C * 2u;
-  const uint32_t plane_bytes = (uint32_t)p.slab_rows * 16u;
+  const uint32_t plane_bytes = ru_plane_bytes(p.slab_rows);
   const uint32_t a_split = planes * plane_bytes;
   const uint32_t a_slot = (a_split * SPLIT + 127u) & ~127u;
   const uint32_t a2_plane = BM * 16u;
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
 size_t ru_smem_bytes(int C, int K, int dil, int split, int nslot) {
   const size_t slab_rows = (BM - 1) + (size_t)(K - 1) * dil + 1;
   const size_t w = (size_t)split * ((size_t)K * C * C * 2 + (size_t)C * C * 2);
-  const size_t a_slot = ((size_t)split * (C / 8) * slab_rows * 16 + 127) & ~size_t(127);
+  const size_t a_slot = ((size_t)split * (C / 8) * ru_plane_bytes((int)slab_rows) + 127) & ~size_t(127);
   const size_t a2_slot = (size_t)split * (C / 8) * BM * 16;
   return w + nslot * (a_slot + a2_slot) + 4 * C * sizeof(float) + STAGE_BYTES + N_BARS * 8 + 64;
 }
@@ -409,8 +417,8 @@ int ru_persist_slots(int C, int K, int dilation, int precision) {
   const char* off = getenv("BC_RU_PERSIST");
   if (off && off[0] == '0') return 0;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
-  if (ru_smem_bytes(C, K, dilation, split, 2) <= 225 * 1024) return 2;
-  if (ru_smem_bytes(C, K, dilation, split, 1) <= 225 * 1024) return 1;
+  if (ru_smem_bytes(C, K, dilation, split, 2) <= 227 * 1024) return 2;
+  if (ru_smem_bytes(C, K, dilation, split, 1) <= 227 * 1024) return 1;
   return 0;
 }
 
@@ -434,7 +442,7 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
   p.trace = g_ru_trace;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
   const size_t smem = ru_smem_bytes(C, K, dilation, split, nslot);
-  if ((size_t)p.slab_rows * 16 * 2 >= (1u << 18)) return fail(BC_EUNSUPPORTED, "resunit(persistent): descriptor offset overflow");
+  if ((size_t)ru_plane_bytes(p.slab_rows) * 2 >= (1u << 18)) return fail(BC_EUNSUPPORTED, "resunit(persistent): descriptor offset overflow");
   void (*kern)(const RuParams) = nullptr;
   const int gi = C == 16 ? 0 : (C == 32 ? 1 : 2);
   if (split == 1) kern = gi == 0 ? ru_persist_kernel<1, 1> : (gi == 1 ? ru_persist_kernel<1, 2> : ru_persist_kernel<1, 4>);
