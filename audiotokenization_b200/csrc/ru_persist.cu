@@ -74,6 +74,27 @@ struct RuParams {
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 10,
        B_ACC2_FULL = 12, B_ACC2_EMPTY = 14, B_W_FULL = 16, N_BARS = 17 };
 
+// r[0 .. 8*n8) += the accumulator columns at `taddr` (the a_hi * w_lo half), 16 columns at a time to bound registers
+__device__ __forceinline__ void add_lo_half(uint32_t taddr, int n8, uint32_t r[32]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (2 * h < n8) {
+      uint32_t t[32];
+      tmem_load(taddr + 16u * h, min(2, n8 - 2 * h), t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (e / 4 + 2 * h < n8) {   // pairs (2e, 2e+1) of this 16-column piece
+          float x0, x1;
+          unpack2(add2(pack2(__uint_as_float(r[16 * h + 2 * e]), __uint_as_float(r[16 * h + 2 * e + 1])),
+                       pack2(__uint_as_float(t[2 * e]), __uint_as_float(t[2 * e + 1]))), x0, x1);
+          r[16 * h + 2 * e] = __float_as_uint(x0);
+          r[16 * h + 2 * e + 1] = __float_as_uint(x1);
+        }
+      }
+    }
+  }
+}
+
 // Stride between the 8-channel planes of the activation slab: rows * 16 B, padded to 16 (mod 128) so that the up to 8
 // planes a warp writes side by side (one 16-byte row chunk each) fall into different banks.
 __host__ __device__ inline uint32_t ru_plane_bytes(int slab_rows) {
@@ -88,6 +109,16 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C;
   const int planes = C / 8;
+  // Split precision, K-tap conv: w_hi and w_lo sit side by side as ONE B operand of 2C rows, so a_hi meets both in a
+  // single MMA of width 2C (accumulator columns [0,C) and [C,2C)) and a_lo * w_hi is a second MMA of width C into
+  // [0,C): with one activation slot the tile period is LOAD-convert + the K-tap MMA chain (trace), and 28 x (64 + 48)
+  // tensor cycles replace 84 x 48 at C = 64.  The MID stage, which is off that critical path, adds the two halves.
+  // The 1x1 conv keeps three MMAs of width C: the STORE stage would otherwise become the longest.
+  constexpr int ACCW = SPLIT == 2 ? 2 : 1;
+  const uint32_t acc1_stage = (uint32_t)(ACCW * p.n_pow2);   // TMEM columns of one K-tap accumulator stage
+  const uint32_t acc2_base = 2u * acc1_stage;                 // the two 1x1 accumulator stages follow
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < acc2_base + 2u * (uint32_t)p.n_pow2) tmem_cols <<= 1;
   const uint32_t w7_split = (uint32_t)p.K * C * C * 2u;
   const uint32_t w1_split = (uint32_t)C * C * 2u;
   const uint32_t plane_bytes = ru_plane_bytes(p.slab_rows);
@@ -122,16 +153,28 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     }
     mbar_init(BAR(B_W_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // resident weights: one expect_tx, copies in <= 32 KB pieces
+    // resident weights: one expect_tx; copies in <= 32 KB pieces, except the split-precision K-tap image, which goes
+    // piece by piece (hi/lo, tap-group, k-plane) so that it lands as [tap-group][k-plane][hi rows | lo rows]
     const uint32_t w7_bytes = w7_split * SPLIT, w1_bytes = w1_split * SPLIT;
     mbar_expect_tx(BAR(B_W_FULL), w7_bytes + w1_bytes);
-    for (uint32_t off = 0; off < w7_bytes; off += 32768u)
-      bulk_g2s_notx(smem_u32(sW7) + off, reinterpret_cast<const uint8_t*>(p.w7) + off, min(32768u, w7_bytes - off), BAR(B_W_FULL));
+    if (SPLIT == 1) {
+      for (uint32_t off = 0; off < w7_bytes; off += 32768u)
+        bulk_g2s_notx(smem_u32(sW7) + off, reinterpret_cast<const uint8_t*>(p.w7) + off, min(32768u, w7_bytes - off), BAR(B_W_FULL));
+    } else {
+      const uint32_t piece = (uint32_t)C * 16u;                 // one k-plane of one tap-group: C rows x 16 B
+      for (int sp = 0; sp < 2; ++sp)
+        for (int kg = 0; kg < p.K * GROUPS; ++kg) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w7) + (size_t)sp * w7_split + (size_t)kg * 2u * piece;
+          const uint32_t dst = smem_u32(sW7) + (uint32_t)kg * 4u * piece + (uint32_t)sp * piece;
+          bulk_g2s_notx(dst, src, piece, BAR(B_W_FULL));                       // k-plane 0
+          bulk_g2s_notx(dst + 2u * piece, src + piece, piece, BAR(B_W_FULL));  // k-plane 1
+        }
+    }
     for (uint32_t off = 0; off < w1_bytes; off += 32768u)
       bulk_g2s_notx(smem_u32(sW1) + off, reinterpret_cast<const uint8_t*>(p.w1) + off, min(32768u, w1_bytes - off), BAR(B_W_FULL));
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(4 * p.n_pow2)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < C; i += RU_THREADS) {
@@ -218,10 +261,11 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       mbar_wait(BAR(B_W_FULL), 0);
       const uint32_t smem0 = smem_u32(smem_raw);
       const uint32_t uW7 = smem0, uW1 = uW7 + w7_split * SPLIT, uA = uW1 + w1_split * SPLIT, uA2 = uA + a_slot * p.nslot;
-      const uint32_t w7_lo0 = desc_lo(uW7, (uint32_t)C * 16u), w1_lo0 = desc_lo(uW1, (uint32_t)C * 16u);
+      const uint32_t w7_lo0 = desc_lo(uW7, (uint32_t)(ACCW * C) * 16u), w1_lo0 = desc_lo(uW1, (uint32_t)C * 16u);
+      const uint32_t idesc_wide = idesc_bf16_m128(ACCW * C);    // [w_hi | w_lo] operand of the K-tap conv
       const uint32_t hi_d = desc_hi(128u);
       const uint32_t a_g = (2u * plane_bytes) >> 4, a_k = (uint32_t)p.dil, a_sp = a_split >> 4;
-      const uint32_t b_g = ((uint32_t)C * 32u) >> 4, b_sp = w7_split >> 4;
+      const uint32_t b_g = ((uint32_t)C * 32u) >> 4, b7_g = ((uint32_t)(ACCW * C) * 32u) >> 4;
       const uint32_t a2_g = (2u * a2_plane) >> 4;
       for (int it = 0; it <= n_my; ++it) {
         if (it < n_my) {  // K-tap conv of tile `it`
@@ -230,7 +274,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
           TRACE(3);
-          const uint32_t d = tmem_base + (uint32_t)(as * p.n_pow2);
+          const uint32_t d = tmem_base + (uint32_t)as * acc1_stage;
           const uint32_t a_lo0 = desc_lo(uA + (uint32_t)slot * a_slot, plane_bytes);
           if (elect_one()) {
 #pragma unroll
@@ -239,13 +283,10 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
 #pragma unroll
                 for (int g = 0; g < GROUPS; ++g) {
                   const uint32_t a_lo = a_lo0 + (uint32_t)k * a_k + (uint32_t)g * a_g;
-                  const uint32_t b_lo = w7_lo0 + (uint32_t)(k * GROUPS + g) * b_g;
-                  if (k == 0 && g == 0) mma_bf16_raw<false>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
-                  else                  mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc);
-                  if (SPLIT == 2) {
-                    mma_bf16_raw<true>(d, a_lo, b_lo + b_sp, hi_d, hi_d, p.idesc);          // a_hi * w_lo
-                    mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);          // a_lo * w_hi
-                  }
+                  const uint32_t b_lo = w7_lo0 + (uint32_t)(k * GROUPS + g) * b7_g;
+                  if (k == 0 && g == 0) mma_bf16_raw<false>(d, a_lo, b_lo, hi_d, hi_d, idesc_wide);   // a_hi * [w_hi | w_lo]
+                  else                  mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, idesc_wide);
+                  if (SPLIT == 2) mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);           // a_lo * w_hi
                 }
               }
             }
@@ -262,7 +303,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
           { const int it = j; TRACE(5); }
-          const uint32_t d = tmem_base + (uint32_t)((2 + as) * p.n_pow2);
+          const uint32_t d = tmem_base + acc2_base + (uint32_t)(as * p.n_pow2);
           const uint32_t a_lo0 = desc_lo(uA2 + (uint32_t)slot * a2_slot, a2_plane);
           if (elect_one()) {
 #pragma unroll
@@ -297,11 +338,12 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       mbar_wait(BAR(B_A2_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
       if (warp == MID_WARP0) TRACE(7);
       uint8_t* dst = sA2 + (size_t)slot * a2_slot + (size_t)row * 16;
-      const uint32_t taddr = tmem_base + (uint32_t)(as * p.n_pow2) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)as * acc1_stage + ((uint32_t)(q * 32) << 16);
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         const int n8 = min(4, (cend - c0) / 8);
         uint32_t r[32];
         tmem_load(taddr + (uint32_t)c0, n8, r);
+        if (SPLIT == 2) add_lo_half(taddr + (uint32_t)(C + c0), n8, r);   // + a_hi * w_lo
         if (c0 + 32 >= cend) {  // this warp's share of the accumulator is read: hand it back before the math
           tc_fence_before();
           __syncwarp();
@@ -346,7 +388,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       float* yp = p.y + off0;
       const size_t istep = (size_t)4 * C;
       const int rows_ok = p.T - trow0 - crow;                // row 4*i of this lane is valid iff 4*i < rows_ok
-      const uint32_t taddr = tmem_base + (uint32_t)((2 + as) * p.n_pow2) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + acc2_base + (uint32_t)(as * p.n_pow2) + ((uint32_t)(q * 32) << 16);
       if (warp == EPI_WARP0) TRACE(9);
       for (int c0 = 0; c0 < C; c0 += 32) {
         const int ncol = min(32, C - c0), n8 = ncol / 8;
@@ -393,7 +435,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(4 * p.n_pow2)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
