@@ -25,13 +25,19 @@ namespace {
 using namespace bc::tc;
 
 constexpr int BM = 128;
-constexpr int LOAD_WARPS = 8;
+#ifndef BC_RU_LOAD_WARPS
+#define BC_RU_LOAD_WARPS 8
+#endif
+#ifndef BC_RU_LD_BATCH
+#define BC_RU_LD_BATCH 5
+#endif
+constexpr int LOAD_WARPS = BC_RU_LOAD_WARPS;
 constexpr int LOAD_THREADS = LOAD_WARPS * 32;
 constexpr int LOAD_GROUPS = 2;                      // loader groups alternate tiles: two tiles' HBM loads in flight
 constexpr int GROUP_WARPS = LOAD_WARPS / LOAD_GROUPS;
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
-constexpr int MMA_WARP = 8;
-constexpr int MID_WARP0 = 9;                        // 8 warps: 2 per TMEM lane quarter (column halves)
+constexpr int MMA_WARP = LOAD_WARPS;
+constexpr int MID_WARP0 = MMA_WARP + 1;                        // 8 warps: 2 per TMEM lane quarter (column halves)
 #ifndef BC_RU_MID_WARPS
 #define BC_RU_MID_WARPS 4
 #endif
@@ -39,7 +45,7 @@ constexpr int MID_WARPS = BC_RU_MID_WARPS;   // 4 (one per TMEM lane quarter) me
 constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;    // 4 warps
 constexpr int RU_WARPS = EPI_WARP0 + 4;
 constexpr int RU_THREADS = RU_WARPS * 32;
-constexpr int LD_BATCH = 5;
+constexpr int LD_BATCH = BC_RU_LD_BATCH;
 constexpr int EPI_LD = 36;                           // staging row stride in floats (32 + 4: conflict-free 16-byte accesses both ways)
 constexpr size_t STAGE_BYTES = (size_t)4 * 32 * EPI_LD * sizeof(float);   // one [32 rows][32 + 4] block per store warp
 
