@@ -57,6 +57,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
   constexpr int LPR = C / 4;                 // lanes (16-byte chunks) per fp32 row
   constexpr int RPI = GT / LPR;              // rows covered by one coalesced group-wide instruction
   constexpr int SLD = C + 4;                 // staging row stride in floats (conflict-free 16-byte accesses both ways)
+  // split precision, K-tap conv: [w_hi | w_lo] as ONE B operand of 2C rows -> a_hi * both in one MMA of width 2C, a_lo * w_hi
+  // in a second of width C (two A fetches per tap-group instead of three: the kernel is bound by shared-memory bandwidth,
+  // most of it the tensor core's operand reads); the mid step adds the two accumulator halves
+  constexpr int ACCW = SPLIT == 2 ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = warp >> 2, gt = tid & (GT - 1), gw = warp & 3;
   const uint32_t w7_split = (uint32_t)p.K * C * C * 2u;
@@ -82,8 +86,19 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t w7_bytes = w7_split * SPLIT, w1_bytes = w1_split * SPLIT;
     mbar_expect_tx(bar_w, w7_bytes + w1_bytes);
-    for (uint32_t off = 0; off < w7_bytes; off += 32768u)
-      bulk_g2s_notx(smem_u32(sW7) + off, reinterpret_cast<const uint8_t*>(p.w7) + off, min(32768u, w7_bytes - off), bar_w);
+    if (SPLIT == 1) {
+      for (uint32_t off = 0; off < w7_bytes; off += 32768u)
+        bulk_g2s_notx(smem_u32(sW7) + off, reinterpret_cast<const uint8_t*>(p.w7) + off, min(32768u, w7_bytes - off), bar_w);
+    } else {   // piece by piece, so that the resident image is [tap-group][k-plane][hi rows | lo rows]
+      const uint32_t piece = (uint32_t)C * 16u;
+      for (int sp = 0; sp < 2; ++sp)
+        for (int kg = 0; kg < p.K * GROUPS; ++kg) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w7) + (size_t)sp * w7_split + (size_t)kg * 2u * piece;
+          const uint32_t dst = smem_u32(sW7) + (uint32_t)kg * 4u * piece + (uint32_t)sp * piece;
+          bulk_g2s_notx(dst, src, piece, bar_w);
+          bulk_g2s_notx(dst + 2u * piece, src + piece, piece, bar_w);
+        }
+    }
     for (uint32_t off = 0; off < w1_bytes; off += 32768u)
       bulk_g2s_notx(smem_u32(sW1) + off, reinterpret_cast<const uint8_t*>(p.w1) + off, min(32768u, w1_bytes - off), bar_w);
   }
@@ -103,7 +118,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
   const uint32_t tmem_base = *tmem_slot;
 
   if (g < p.G) {
-    const uint32_t acc1 = tmem_base + (uint32_t)(2 * g * p.n_pow2), acc2 = acc1 + (uint32_t)p.n_pow2;
+    const uint32_t acc1 = tmem_base + (uint32_t)((ACCW + 1) * g * p.n_pow2), acc2 = acc1 + (uint32_t)(ACCW * p.n_pow2);
     const uint32_t taddr_lane = (uint32_t)(gw * 32) << 16;      // this warp's TMEM lane quarter
     const int row = gw * 32 + lane;                              // accumulator row of this thread
     // staging geometry (LOAD): thread -> (plane, row offset)
@@ -119,10 +134,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
     const int crow = gt / LPR, cchunk = (gt % LPR) * 4;
     float* sT = reinterpret_cast<float*>(sG);
     const uint32_t hi_d = desc_hi(128u);
-    const uint32_t w7_lo0 = desc_lo(smem_u32(sW7), (uint32_t)C * 16u), w1_lo0 = desc_lo(smem_u32(sW1), (uint32_t)C * 16u);
+    const uint32_t w7_lo0 = desc_lo(smem_u32(sW7), (uint32_t)(ACCW * C) * 16u), w1_lo0 = desc_lo(smem_u32(sW1), (uint32_t)C * 16u);
+    const uint32_t idesc_wide = idesc_bf16_m128(ACCW * C);
     const uint32_t a_lo0 = desc_lo(smem_u32(sA), plane_bytes), a2_lo0 = desc_lo(smem_u32(sA2), a2_plane);
     const uint32_t a_g = (2u * plane_bytes) >> 4, a_k = (uint32_t)p.dil, a_sp = a_split >> 4;
-    const uint32_t b_g = ((uint32_t)C * 32u) >> 4, b_sp = w7_split >> 4, a2_g = (2u * a2_plane) >> 4;
+    const uint32_t b_g = ((uint32_t)C * 32u) >> 4, b7_g = ((uint32_t)(ACCW * C) * 32u) >> 4, a2_g = (2u * a2_plane) >> 4;
 
     const int tstep = (int)gridDim.x * p.G;
     int tile = (int)blockIdx.x * p.G + g;
@@ -176,13 +192,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
 #pragma unroll
               for (int gg = 0; gg < GROUPS; ++gg) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)k * a_k + (uint32_t)gg * a_g;
-                const uint32_t b_lo = w7_lo0 + (uint32_t)(k * GROUPS + gg) * b_g;
-                if (k == 0 && gg == 0) mma_bf16_raw<false>(acc1, a_lo, b_lo, hi_d, hi_d, p.idesc);
-                else                   mma_bf16_raw<true>(acc1, a_lo, b_lo, hi_d, hi_d, p.idesc);
-                if (SPLIT == 2) {
-                  mma_bf16_raw<true>(acc1, a_lo, b_lo + b_sp, hi_d, hi_d, p.idesc);
-                  mma_bf16_raw<true>(acc1, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);
-                }
+                const uint32_t b_lo = w7_lo0 + (uint32_t)(k * GROUPS + gg) * b7_g;
+                if (k == 0 && gg == 0) mma_bf16_raw<false>(acc1, a_lo, b_lo, hi_d, hi_d, idesc_wide);   // a_hi * [w_hi | w_lo]
+                else                   mma_bf16_raw<true>(acc1, a_lo, b_lo, hi_d, hi_d, idesc_wide);
+                if (SPLIT == 2) mma_bf16_raw<true>(acc1, a_lo + a_sp, b_lo, hi_d, hi_d, p.idesc);            // a_lo * w_hi
               }
             }
           }
@@ -208,6 +221,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
         for (int c0 = 0; c0 < C; c0 += 32) {
           uint32_t r[32];
           tmem_load32(acc1 + taddr_lane + (uint32_t)c0, r);
+          if (SPLIT == 2) {   // + a_hi * w_lo, 16 columns at a time
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t t[32];
+              tmem_load(acc1 + taddr_lane + (uint32_t)(C + c0 + 16 * h), 2, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x0, x1;
+                unpack2(add2(pack2(__uint_as_float(r[16 * h + 2 * e]), __uint_as_float(r[16 * h + 2 * e + 1])),
+                             pack2(__uint_as_float(t[2 * e]), __uint_as_float(t[2 * e + 1]))), x0, x1);
+                r[16 * h + 2 * e] = __float_as_uint(x0);
+                r[16 * h + 2 * e + 1] = __float_as_uint(x1);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = c0 + 8 * j;
@@ -305,7 +333,7 @@ bool rg_plan(int C, int K, int dilation, int precision, RgPlan* pl) {
   int G = (int)((225 * 1024 - fixed) / group);
   if (G > MAX_G) G = MAX_G;
   const int n_pow2 = C <= 32 ? 32 : 64;
-  if (G > 512 / (2 * n_pow2)) G = 512 / (2 * n_pow2);            // two accumulators per group in 512 TMEM columns
+  if (G > 512 / ((split + 1) * n_pow2)) G = 512 / ((split + 1) * n_pow2);   // K-tap accumulator (x2 in split precision: hi | lo halves) + 1x1 accumulator per group in 512 TMEM columns
   if (G < 3) return false;                                       // with fewer groups the role pipeline of ru_persist is better
   pl->G = G; pl->split = split; pl->a_bytes = (uint32_t)a; pl->group_bytes = (uint32_t)group;
   pl->smem = fixed + (size_t)G * group;
@@ -342,7 +370,7 @@ int resunit_group_fwd(const float* x, const float* w7, const float* b7, const fl
   p.total_tiles = (int)total;
   p.G = pl.G;
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * pl.G * p.n_pow2) p.tmem_cols <<= 1;   // power of two >= 32
+  while (p.tmem_cols < (pl.split + 1) * pl.G * p.n_pow2) p.tmem_cols <<= 1;   // power of two >= 32
   p.idesc = idesc_bf16_m128(C);
   p.group_bytes = pl.group_bytes;
   p.a_bytes = pl.a_bytes;
