@@ -202,3 +202,63 @@ def test_stream_weight_image_layout():
     assert hi == w[k, ci, co].to(torch.bfloat16).float()
     assert abs(float(hi + lo - w[k, ci, co])) <= 2.0 ** -16 * abs(float(w[k, ci, co])) + 1e-12
     assert tuple(ops.pack_stream_weight(w, N, "bf16").shape) == (cout // N, cin // 16, K, 1, 2, N, 8)
+
+
+class _FakeEncoder:
+    """Stand-in for BigCodecEncoder with the two-stage front-end interface, pure CPU tensors: shallow = x * 2 over
+    [b, T, 1] -> [b, T // 2, 4], deep = sum over channels -> [b, T // 2, 1].  Records the batch sizes each stage saw."""
+
+    def __init__(self):
+        self.shallow_batches, self.deep_batches, self.whole_batches = [], [], []
+
+    def front_shallow_cl(self, x_cl, out=None):
+        self.shallow_batches.append(x_cl.shape[0])
+        y = (x_cl[:, ::2, :] * 2.0).expand(-1, -1, 4).contiguous()
+        if out is None:
+            return y
+        assert out.shape == y.shape and out.is_contiguous()
+        out.copy_(y)
+        return out
+
+    def front_deep_cl(self, h):
+        self.deep_batches.append(h.shape[0])
+        return h.sum(dim=2, keepdim=True)
+
+    def front_cl(self, x_cl):
+        self.whole_batches.append(x_cl.shape[0])
+        return self.front_deep_cl(self.front_shallow_cl(x_cl))
+
+
+@pytest.mark.parametrize("sizes,deep,expect_deep", [
+    ([2, 2, 2, 2], 4, [4, 4]),          # buffer fills exactly
+    ([2, 2, 2], 5, [4, 2]),             # 2+2 | 2: a push that does not fit flushes first
+    ([3, 3, 1], 64, [7]),               # never full: one deep launch at take()
+    ([1], 2, [1]),
+])
+def test_front_pipeline_gathers_micro_batches_in_order(sizes, deep, expect_deep):
+    """model._FrontPipeline: shallow stage per micro-batch into slices of one hand-off buffer, deep stage when it is full
+    or at take(); the concatenated result keeps push order and equals the un-staged front end."""
+    from audiotokenization_b200.model import _FrontPipeline
+    enc = _FakeEncoder()
+    pipe = _FrontPipeline(enc, deep)
+    T = 10
+    xs = [torch.arange(b * T, dtype=torch.float32).view(b, T, 1) + 100 * i for i, b in enumerate(sizes)]
+    for x in xs:
+        pipe.push(x)
+    got = pipe.take()
+    want = torch.cat([_FakeEncoder().front_cl(x) for x in xs], dim=0)
+    assert torch.equal(got, want)
+    assert enc.shallow_batches == sizes and enc.deep_batches == expect_deep and enc.whole_batches == []
+    # the pipeline is reusable after take(): second group, same buffer
+    pipe.push(xs[0])
+    assert torch.equal(pipe.take(), want[: sizes[0]])
+
+
+def test_front_pipeline_without_gathering_uses_the_plain_front_end():
+    from audiotokenization_b200.model import _FrontPipeline
+    enc = _FakeEncoder()
+    pipe = _FrontPipeline(enc, 2)          # deep_batch <= micro-batch: nothing to gather
+    x = torch.ones(2, 6, 1)
+    pipe.push(x)
+    pipe.push(x)
+    assert pipe.take().shape == (4, 3, 1) and enc.whole_batches == [2, 2]
