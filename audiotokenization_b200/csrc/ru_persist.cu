@@ -37,7 +37,7 @@ constexpr int LOAD_GROUPS = 2;                      // loader groups alternate t
 constexpr int GROUP_WARPS = LOAD_WARPS / LOAD_GROUPS;
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 constexpr int MMA_WARP = LOAD_WARPS;
-constexpr int MID_WARP0 = MMA_WARP + 1;                        // 8 warps: 2 per TMEM lane quarter (column halves)
+constexpr int MID_WARP0 = MMA_WARP + 4;             // the MMA warp shares its warpgroup with three idle warps (setmaxnreg works on warpgroups)
 #ifndef BC_RU_MID_WARPS
 #define BC_RU_MID_WARPS 4
 #endif
@@ -45,6 +45,10 @@ constexpr int MID_WARPS = BC_RU_MID_WARPS;   // 4 (one per TMEM lane quarter) me
 constexpr int EPI_WARP0 = MID_WARP0 + MID_WARPS;    // 4 warps
 constexpr int RU_WARPS = EPI_WARP0 + 4;
 constexpr int RU_THREADS = RU_WARPS * 32;
+static_assert(LOAD_WARPS % 4 == 0 && MID_WARPS % 4 == 0, "roles must fill whole warpgroups");
+// Register budget after launch (96 per thread for 20 warps): the MMA warpgroup keeps 40, the loaders (raw tile in
+// registers while they wait for the slot) take 120, the store warps 104.  (5 x 96 = 2 x 120 + 40 + 96 + 104)
+constexpr int REG_MMA = 56, REG_LOAD = 112, REG_STORE = 104;
 constexpr int LD_BATCH = BC_RU_LD_BATCH;
 constexpr int EPI_LD = 36;                           // staging row stride in floats (32 + 4: conflict-free 16-byte accesses both ways)
 constexpr size_t STAGE_BYTES = (size_t)4 * 32 * EPI_LD * sizeof(float);   // one [32 rows][32 + 4] block per store warp
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
 
   if (warp < LOAD_WARPS) {
     // ======================= LOAD =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_LOAD));
     const int items = planes * p.slab_rows;
     // two slots: the loader groups take alternate tiles (group g always fills slot g, so a producer is never
     // more than one mbarrier phase ahead); one slot: all 8 warps stage every tile together
@@ -257,7 +262,9 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
       if (gtid == 0) TRACE(2);
       if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp < MID_WARP0) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_MMA));
+   if (warp == MMA_WARP) {
     // ======================= MMA issue =======================
     // All address arithmetic below is built from kernel parameters, blockIdx and loop counters only, so it
     // stays in uniform registers; one elected lane issues a whole tile's MMAs back to back.
@@ -330,6 +337,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
         }
       }
     }
+   }
   } else if (warp < EPI_WARP0) {
     // ======================= MID: acc1 -> snake2 -> bf16 A2 tile =======================
     const int q = warp & 3;
@@ -376,6 +384,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
     }
   } else {
     // ======================= STORE: acc2 + b1 + x -> y =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_STORE));
     // The accumulator arrives one row per lane; a lane-per-row global access costs 32 L1 wavefronts per instruction
     // (the L1 data pipe was 92 % busy and the bound of this kernel).  Each warp owns a padded [32 rows][32 + 4] fp32
     // block: bias-added rows go in, and leave with 8 lanes per row (4 whole lines per instruction); the residual is
