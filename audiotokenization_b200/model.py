@@ -33,15 +33,19 @@ class _FrontPipeline:
 
     def __init__(self, encoder, deep_batch: int):
         self.enc, self.cap = encoder, int(deep_batch)
-        self.buf, self.fill, self.feats = None, 0, []
+        self.buf, self.fill, self.feats, self.t_in = None, 0, [], None
 
     def push(self, x_cl: torch.Tensor) -> None:
         b = x_cl.shape[0]
         if self.cap <= b:                                   # nothing to gather
             self.feats.append(self.enc.front_cl(x_cl))
             return
+        if self.t_in is not None and x_cl.shape[1] != self.t_in:   # another clip length: new hand-off geometry
+            self.flush()
+            self.buf = None
         if self.fill + b > self.cap:
             self.flush()
+        self.t_in = x_cl.shape[1]
         if self.buf is None:
             y = self.enc.front_shallow_cl(x_cl)
             self.buf = torch.empty((self.cap,) + tuple(y.shape[1:]), device=y.device, dtype=y.dtype)

@@ -262,3 +262,18 @@ def test_front_pipeline_without_gathering_uses_the_plain_front_end():
     pipe.push(x)
     pipe.push(x)
     assert pipe.take().shape == (4, 3, 1) and enc.whole_batches == [2, 2]
+
+
+def test_front_pipeline_flushes_when_the_clip_length_changes():
+    """Equal-length groups of different lengths may share one pipeline: the hand-off buffer is re-made, results of a
+    take() can then only be returned per length (features of different lengths do not concatenate)."""
+    from audiotokenization_b200.model import _FrontPipeline
+    enc = _FakeEncoder()
+    pipe = _FrontPipeline(enc, 8)
+    a, b = torch.ones(2, 10, 1), torch.ones(3, 6, 1)
+    pipe.push(a)
+    fa = pipe.take()
+    pipe.push(b)                       # different T after a take(): buffer must be re-allocated, not reused
+    fb = pipe.take()
+    assert fa.shape == (2, 5, 1) and fb.shape == (3, 3, 1)
+    assert enc.deep_batches == [2, 3]
