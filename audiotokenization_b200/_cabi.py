@@ -25,6 +25,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
 _SIGNATURES = {
     "bc_abi_version": (c_int, []),
     "bc_last_error": (c_char_p, []),
+    "bc_policy": (c_int, [c_char_p, c_size_t]),
     "bc_device_info": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     "bc_transpose_bct_to_btc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "bc_transpose_btc_to_bct": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -72,10 +73,17 @@ def load_library() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.bc_abi_version() != 3:
-        raise RuntimeError(f"stale {LIB_PATH}: ABI {lib.bc_abi_version()} != 3; rebuild")
+    if lib.bc_abi_version() != 4:
+        raise RuntimeError(f"stale {LIB_PATH}: ABI {lib.bc_abi_version()} != 4; rebuild")
     _lib = lib
     return lib
+
+
+def policy() -> str:
+    """The kernel-selection knobs the library read from the environment (once, at first use)."""
+    buf = ctypes.create_string_buffer(256)
+    check(load_library().bc_policy(buf, 256), "bc_policy")
+    return buf.value.decode()
 
 
 def last_error() -> str:

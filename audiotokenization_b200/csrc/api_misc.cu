@@ -1,6 +1,7 @@
 // Error plumbing, device query, layout transforms.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace bc {
 static thread_local char g_err[512] = "";
@@ -10,7 +11,34 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static Policy read_policy() {
+  Policy p;
+  const char* e;
+  e = getenv("BC_TC_VARIANT");   p.tc_variant = e ? atoi(e) & 3 : 0;
+  e = getenv("BC_TC_PERSIST");   p.tc_persist = (e && e[0] == '1') ? 1 : 0;
+  e = getenv("BC_RU_GROUP");     p.ru_group = (e && e[0] == '0') ? 0 : 1;
+  e = getenv("BC_RU_PERSIST");   p.ru_persist = (e && e[0] == '0') ? 0 : 1;
+  e = getenv("BC_LSTM_PINGPONG"); p.lstm_pingpong = (e && e[0] == '0') ? 0 : 1;
+  return p;
+}
+const Policy& policy() {
+  static const Policy p = read_policy();   // thread-safe one-time initialisation
+  return p;
+}
 }  // namespace bc
+
+extern "C" int bc_policy(char* buf, size_t n) {
+  if (!buf || n == 0) return bc::fail(BC_EINVAL, "bc_policy: null buffer");
+  const bc::Policy& p = bc::policy();
+#ifdef BC_TRACE
+  const int trace = 1;
+#else
+  const int trace = 0;
+#endif
+  snprintf(buf, n, "tc_variant=%d tc_persist=%d ru_group=%d ru_persist=%d lstm_pingpong=%d trace_build=%d", p.tc_variant,
+           p.tc_persist, p.ru_group, p.ru_persist, p.lstm_pingpong, trace);
+  return BC_OK;
+}
 
 extern "C" int bc_abi_version(void) { return BC_ABI_VERSION; }
 extern "C" const char* bc_last_error(void) { return bc::g_err; }

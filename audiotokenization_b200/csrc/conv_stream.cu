@@ -117,9 +117,20 @@ struct SParams {
   uint32_t idesc;
   int tmem_cols;
   long long* trace;   // debug: [tile_it < 64][16] clock64 stamps / wait totals of CTA 0 (NULL = off)
+#ifdef BC_TRACE
   int dbg_skip;     // timing experiment bits: 1 producers skip loads+math, 2 MID skips math, 4 STORE skips global traffic
   int dbg_bshift;   // timing experiment: copy only 1/2^n of every weight unit (results are wrong)
+#endif
 };
+// The timing experiments above produce WRONG results by design; they exist only in -DBC_TRACE builds
+// (BC_TRACE=1 python -m audiotokenization_b200.build), never in the product library.
+#ifdef BC_TRACE
+#define DBG_SKIP(bits) ((p.dbg_skip & (bits)) != 0)
+#define DBG_BSHIFT (p.dbg_bshift)
+#else
+#define DBG_SKIP(bits) false
+#define DBG_BSHIFT 0
+#endif
 
 // 4 fp32 values -> bf16 hi (and lo = v - hi) halves of a 16-byte K-major row chunk
 template <int SPLIT>
@@ -233,8 +244,8 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
   int n_my = 0;
   for (int tile = first; tile < p.total_tiles; tile += step) ++n_my;
 
-  const bool freerun = (p.dbg_skip & 8) != 0;      // timing experiment: MMA thread free-runs on whatever is in smem
-  const bool free_b = (p.dbg_skip & 16) != 0;      // ... only the weight ring is ignored
+  const bool freerun = DBG_SKIP(8);      // timing experiment: MMA thread free-runs on whatever is in smem
+  const bool free_b = DBG_SKIP(16);      // ... only the weight ring is ignored
   if (warp < N_PROD) {
     if (R::REG_PROD < R::REG_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_PROD));
     if (freerun) goto done;
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         const float* xcol = xb + g * 16;
         uint8_t* dst = sA + (size_t)slot * p.a_stage + dst_off;
         bool waited = false;
-        if (p.stride == 1 && g0row >= 0 && g0row + p.slab_rows <= p.T_in && !(p.dbg_skip & 1)) {
+        if (p.stride == 1 && g0row >= 0 && g0row + p.slab_rows <= p.T_in && !DBG_SKIP(1)) {
           // interior tile of an un-strided conv (almost every tile): no bounds tests, pointers advance by constants
           const float* src = xcol + (size_t)(g0row + r_first) * p.C_in;
           const size_t rstride = (size_t)rstep * p.C_in;
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
           // incrementally from the thread's constant first row
           const bool inside = g0row >= 0 && g0row + p.slab_rows <= p.T_in;
           int ph = ph_first, rr = rr_first;
-          for (int r0 = r_first; r0 < p.slab_rows && !(p.dbg_skip & 1); r0 += rstep * P_BATCH) {
+          for (int r0 = r_first; r0 < p.slab_rows && !DBG_SKIP(1); r0 += rstep * P_BATCH) {
             float4 v4[P_BATCH];
 #pragma unroll
             for (int j = 0; j < P_BATCH; ++j) {
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
             for (int u = 0; u < p.upg; ++u) {
               const int k0 = u * p.tpu, k1 = min(p.K, k0 + p.tpu);
               mbar_wait(BAR(B_B_EMPTY + slot), phase);
-              bulk_g2s(uB + slot * p.unit_bytes, wnt + (size_t)(g * p.K + k0) * p.tap_bytes, ((uint32_t)(k1 - k0) * p.tap_bytes) >> p.dbg_bshift,
+              bulk_g2s(uB + slot * p.unit_bytes, wnt + (size_t)(g * p.K + k0) * p.tap_bytes, ((uint32_t)(k1 - k0) * p.tap_bytes) >> DBG_BSHIFT,
                        BAR(B_B_FULL + slot));
               if (++slot == (uint32_t)p.NB) { slot = 0; phase ^= 1u; }
             }
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
             for (int c = 0; c < nchunk; ++c)
               for (int gu = 0; gu < 4 / p.gpu1; ++gu) {
                 mbar_wait(BAR(B_B_EMPTY + slot), phase);
-                bulk_g2s(uB + slot * p.unit_bytes, p.w1 + (size_t)(c * 4 + gu * p.gpu1) * p.tap_bytes, ((uint32_t)p.gpu1 * p.tap_bytes) >> p.dbg_bshift,
+                bulk_g2s(uB + slot * p.unit_bytes, p.w1 + (size_t)(c * 4 + gu * p.gpu1) * p.tap_bytes, ((uint32_t)p.gpu1 * p.tap_bytes) >> DBG_BSHIFT,
                          BAR(B_B_FULL + slot));
                 if (++slot == (uint32_t)p.NB) { slot = 0; phase ^= 1u; }
               }
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
             if (hh == 0) mbar_wait(BAR(B_A2_EMPTY + s2), (u2 & 1u) ^ 1u);
             uint8_t* dst = sA2 + (size_t)s2 * a2_chunk + (size_t)(hcol * 4) * A2_PLANE + (size_t)row * 16;
 #pragma unroll
-            for (int j = 0; j < ((p.dbg_skip & 2) ? 0 : 4); ++j) {
+            for (int j = 0; j < (DBG_SKIP(2) ? 0 : 4); ++j) {
               const int ch = cbase + 8 * j;
               const float4 bi0 = *reinterpret_cast<const float4*>(sPar + ch), bi1 = *reinterpret_cast<const float4*>(sPar + ch + 4);
               const float4 s0 = *reinterpret_cast<const float4*>(sPar + p.N + ch), s1 = *reinterpret_cast<const float4*>(sPar + p.N + ch + 4);
@@ -602,7 +613,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       const int nt = tp.nt, b = tp.b;
       const int trow0 = tp.tt * BM + q * 32;     // first output row of this warp's block
       const size_t off0 = ((size_t)b * p.T_out + trow0 + crow) * p.C_out + (size_t)nt * p.N + cchunk;
-      const float* rp = (p.res && !(p.dbg_skip & 4)) ? p.res + off0 : nullptr;
+      const float* rp = (p.res && !DBG_SKIP(4)) ? p.res + off0 : nullptr;
       float* yp = p.y + off0;
       const size_t istep = (size_t)4 * p.C_out;                         // 4 rows further per load/store instruction
       const int rows_ok = p.T_out - trow0 - crow;                      // row 4*i of this lane is valid iff 4*i < rows_ok
@@ -659,7 +670,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
           *reinterpret_cast<float4*>(own + 4 * j) = v;
         }
         __syncwarp();
-        if (!(p.dbg_skip & 4)) {
+        if (!DBG_SKIP(4)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(sT + (4 * i + crow) * EPI_LD + cchunk);
@@ -774,8 +785,10 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) 
   p.total_tiles = (int)total;
   p.idesc = idesc_bf16_m128(pl.N);
   p.trace = g_stream_trace;
-  { const char* e = getenv("BC_STREAM_BSHIFT"); p.dbg_bshift = e ? atoi(e) : 0; }
+#ifdef BC_TRACE
+  { const char* e = getenv("BC_STREAM_BSHIFT"); p.dbg_bshift = e ? (atoi(e) & 15) : 0; }
   { const char* e = getenv("BC_STREAM_SKIP"); p.dbg_skip = e ? atoi(e) : 0; }
+#endif
   void (*kern)(const SParams) = nullptr;
   int slot = 0;
   if (pl.split == 1 && !fused) { kern = conv_stream_kernel<1, false>; slot = 0; }

@@ -339,8 +339,7 @@ static int launch_tc(TcParams& p, int precision, cudaStream_t st) {
   p.rpp = (p.slab_rows + p.stride - 1) / p.stride;
   p.tmem_cols = p.fuse2 ? 2 * pow2_cols(p.n_tile) : pow2_cols(p.n_tile);
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  const char* var = getenv("BC_TC_VARIANT");
-  p.variant = var ? atoi(var) : 0;
+  p.variant = bc::policy().tc_variant;
   const size_t a_bytes = (size_t)p.split * 2 * p.gpc * p.stride * p.rpp * 16;
   const size_t b_bytes = (size_t)p.split * p.K * p.gpc * p.n_tile * 32;
   size_t region1 = ((a_bytes + 127) & ~size_t(127)) + ((b_bytes + 127) & ~size_t(127));
@@ -355,9 +354,8 @@ static int launch_tc(TcParams& p, int precision, cudaStream_t st) {
   if (total_tiles > 2147483647ll) return fail(BC_EINVAL, "conv1d(tensor-core): too many tiles");
   p.total_tiles = (int)total_tiles;
   // persistent mode: one chunk, one n-tile, and (fused) the intermediate must fit inside the slab region alone
-  const char* pm = getenv("BC_TC_PERSIST");
   p.persist = (p.nchunks == 1 && p.C_out == p.n_tile && (!p.fuse2 || a2 <= ((a_bytes + 127) & ~size_t(127))) &&
-               (pm && pm[0] == '1')) ? 1 : 0;   // opt-in: measured slower than the one-tile-per-CTA schedule
+               bc::policy().tc_persist) ? 1 : 0;   // opt-in: measured slower than the one-tile-per-CTA schedule
   p.region1_bytes = (uint32_t)region1;
   const size_t smem = region1 + b2 + 64;
   if (smem > 227 * 1024) return fail(BC_EUNSUPPORTED, "conv1d(tensor-core): tile needs %zu B of shared memory", smem);

@@ -45,11 +45,15 @@ struct LstmTcParams {
 #define LTRACE(ev) do { } while (0)
 #endif
 
+// Gate non-linearities of the tensor-core modes: SFU exp + approximate divide (|error| ~ 2e-7, far below the
+// bf16x3 operand error; the fp32 mode runs lstm.cu with expf / tanhf).  Both saturate correctly for ANY finite
+// input: the cell state is unbounded (c grows by up to 1 per step), so tanh must not produce inf/inf.
+//   sigmoid: exp(-x) -> +inf for x < -88 and __fdividef(1, inf) = 0; exp(-x) -> 0 for x > 88 gives 1.
+//   tanh:    evaluated on |x| (e = exp(-2|x|) in (0, 1], denominator in [1, 2]) and the sign restored.
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
-  // 2*sigmoid(2x) - 1, evaluated so that the result is exact-ish near 0: (1 - e) / (1 + e), e = exp(-2x)
-  const float e = __expf(-2.f * x);
-  return __fdividef(1.f - e, 1.f + e);
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
 template <int SPLIT, int UPW>

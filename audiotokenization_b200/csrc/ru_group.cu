@@ -346,8 +346,7 @@ namespace bc {
 
 // 0 = not applicable, else the number of warpgroups per CTA
 int ru_group_groups(int C, int K, int dilation, int precision) {
-  const char* off = getenv("BC_RU_GROUP");
-  if (off && off[0] == '0') return 0;
+  if (!policy().ru_group) return 0;
   RgPlan pl;
   return rg_plan(C, K, dilation, precision, &pl) ? pl.G : 0;
 }

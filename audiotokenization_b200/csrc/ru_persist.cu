@@ -471,8 +471,7 @@ static long long* g_ru_trace = nullptr;
 // 0 = not applicable, else number of smem operand slots the persistent kernel would use
 int ru_persist_slots(int C, int K, int dilation, int precision) {
   if ((C != 16 && C != 32 && C != 64) || K > 7) return 0;   // power-of-two plane count; weights must stay resident
-  const char* off = getenv("BC_RU_PERSIST");
-  if (off && off[0] == '0') return 0;
+  if (!policy().ru_persist) return 0;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
   if (ru_smem_bytes(C, K, dilation, split, 2) <= 227 * 1024) return 2;
   if (ru_smem_bytes(C, K, dilation, split, 1) <= 227 * 1024) return 1;

@@ -94,33 +94,72 @@ def prepare_waveform(waveform: torch.Tensor, sample_rate: int, target_sample_rat
 
 def extract_to_directory(model, items: Iterable[Tuple[torch.Tensor, str, str]], output_dir: str, *,
                          micro_batch: int = 8, rnn_batch: int = 256, group_size: int = 256, writers: int = 4,
+                         max_buffered_bytes: int = 2 << 30, max_buffered_items: int = 4096,
                          verbose: bool = True) -> Tuple[int, int]:
     """Encode ``items`` = (waveform float32 [T] or [1, T] at the codec rate, subset, fileid) and write one ``.npy``
     per utterance in the reference's layout.  Returns (saved, errors) like the counters of extract_indices.py:492-579.
 
     Utterances are encoded in groups of equal length (up to ``group_size``), each group through
-    ``model.extract_indices`` (pinned host buffer, H2D overlapped with compute); a failing utterance or group is
-    reported and skipped, never fatal.  File writes run on ``writers`` threads."""
+    ``model.extract_indices`` (pinned host buffer, H2D overlapped with compute).  The buffer of waiting
+    utterances is bounded: once it holds more than ``max_buffered_bytes`` of samples or ``max_buffered_items``
+    utterances, the largest waiting group is encoded -- with full-length files (``duration=None``, the reference's
+    default) almost every length is unique, and an unbounded buffer would hold the whole corpus before the first
+    encode.  A failing group is retried one utterance at a time, so one bad utterance costs one error like in the
+    reference (extract_indices.py:565-574), never a whole group.  File writes run on ``writers`` threads and are
+    reaped as they complete."""
     saved = errors = 0
     pending = []
     groups = {}
+    buffered_bytes = buffered_items = 0
+
+    def reap(block: bool) -> None:
+        nonlocal saved, errors, pending
+        keep = []
+        for fileid, fut in pending:
+            if not block and not fut.done():
+                keep.append((fileid, fut))
+                continue
+            try:
+                fut.result()
+                saved += 1
+            except Exception as e:
+                print(f"\nError saving indices of {fileid}: {e}")
+                errors += 1
+        pending = keep
+
+    def encode(batch, length):
+        host = torch.empty((len(batch), 1, length), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        for i, (w, _, _) in enumerate(batch):
+            host[i, 0] = w
+        return model.extract_indices(host, micro_batch=micro_batch, rnn_batch=rnn_batch)   # [N, T', n_q]
 
     def flush(length):
-        nonlocal saved, errors
+        nonlocal errors, buffered_bytes, buffered_items
         batch = groups.pop(length, [])
         if not batch:
             return
+        buffered_bytes -= 4 * length * len(batch)
+        buffered_items -= len(batch)
         try:
-            host = torch.empty((len(batch), 1, length), dtype=torch.float32, pin_memory=torch.cuda.is_available())
-            for i, (w, _, _) in enumerate(batch):
-                host[i, 0] = w
-            i16 = model.extract_indices(host, micro_batch=micro_batch, rnn_batch=rnn_batch)   # [N, T', n_q]
-        except Exception as e:   # the reference swallows per-utterance errors (extract_indices.py:565-574)
-            print(f"\nError processing a group of {len(batch)} utterances of {length} samples: {e}")
-            errors += len(batch)
-            return
-        for i, (_, subset, fileid) in enumerate(batch):
-            pending.append((fileid, pool.submit(save_indices, output_dir, subset, fileid, i16[i])))
+            results = list(encode(batch, length))
+        except Exception as e:
+            if len(batch) == 1:
+                print(f"\nError processing {batch[0][2]}: {e}")
+                errors += 1
+                return
+            print(f"\nError processing a group of {len(batch)} utterances of {length} samples: {e}; retrying one by one")
+            results = []
+            for item in batch:
+                try:
+                    results.append(encode([item], length)[0])
+                except Exception as e1:   # the reference swallows per-utterance errors (extract_indices.py:565-574)
+                    print(f"\nError processing {item[2]}: {e1}")
+                    errors += 1
+                    results.append(None)
+        for (_, subset, fileid), arr in zip(batch, results):
+            if arr is not None:
+                pending.append((fileid, pool.submit(save_indices, output_dir, subset, fileid, arr)))
+        reap(block=False)
 
     with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
         for item in items:
@@ -133,18 +172,17 @@ def extract_to_directory(model, items: Iterable[Tuple[torch.Tensor, str, str]], 
                 print(f"\nError processing batch item: {e}")
                 errors += 1
                 continue
-            groups.setdefault(w.numel(), []).append((w, subset, fileid))
-            if len(groups[w.numel()]) >= group_size:
-                flush(w.numel())
+            n = w.numel()
+            groups.setdefault(n, []).append((w, subset, fileid))
+            buffered_bytes += 4 * n
+            buffered_items += 1
+            if len(groups[n]) >= group_size:
+                flush(n)
+            while buffered_bytes > max_buffered_bytes or buffered_items > max_buffered_items:
+                flush(max(groups, key=lambda k: (k * len(groups[k]), -k)))     # the group holding the most samples
         for length in sorted(groups):
             flush(length)
-        for fileid, fut in pending:
-            try:
-                fut.result()
-                saved += 1
-            except Exception as e:
-                print(f"\nError saving indices of {fileid}: {e}")
-                errors += 1
+        reap(block=True)
     if verbose:
         print("\nExtraction complete.")
         print(f"Successfully saved {saved} index files.")

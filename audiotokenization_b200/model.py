@@ -80,26 +80,72 @@ class BigCodecModel(nn.Module):
         if dec_state is not None:
             self.decoder.load_state_dict(dec_state, strict=True)
         self.codebook_size = cfg["codec_decoder"]["codebook_size"]
-        self.precision = precision
+        self.precision = precision      # property: also stored on encoder / decoder (direct sub-module calls honour it)
         self.to(device)
         self.eval()
 
+    @property
+    def precision(self) -> str:
+        return self._precision
+
+    @precision.setter
+    def precision(self, mode: str) -> None:
+        if mode not in ops.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)}")
+        self._precision = mode
+        self.encoder.precision = mode
+        self.decoder.precision = mode
+
     # -- checkpoint adapter (extract_indices.py:309-323) ---------------------------------
+    # prefixes under which checkpoints carry the codec's two modules: the Lightning module's attribute names
+    # (SURVEY.md section 5), the wrappers' ``lm.model[...]`` names, both optionally DataParallel-wrapped
+    _CKPT_PREFIXES = (("encoder.", "decoder."), ("model.CodecEnc.", "model.generator."), ("CodecEnc.", "generator."))
+
+    @classmethod
+    def split_checkpoint(cls, ckpt) -> tuple:
+        """(encoder state dict, decoder state dict, number of other keys) from a loaded checkpoint object:
+        ``{'state_dict': ...}`` (Lightning), ``{'model': ...}`` or a bare state dict (extract_indices.py:309-315)."""
+        sd = ckpt
+        if isinstance(ckpt, dict):
+            if "state_dict" in ckpt:
+                sd = ckpt["state_dict"]
+            elif "model" in ckpt and isinstance(ckpt["model"], dict):
+                sd = ckpt["model"]
+        if not isinstance(sd, dict) or not sd:
+            raise ValueError("checkpoint holds no state dict")
+        for lead in ("", "module.", "lm.", "lm.module."):
+            for pe, pd in cls._CKPT_PREFIXES:
+                enc, dec = _strip_prefix(sd, lead + pe), _strip_prefix(sd, lead + pd)
+                if enc and dec:
+                    return enc, dec, len(sd) - len(enc) - len(dec)
+        raise ValueError("checkpoint has no encoder/decoder entries under any known prefix "
+                         f"({', '.join(a + '|' + b for a, b in cls._CKPT_PREFIXES)}); first keys: {list(sd)[:4]}")
+
     @classmethod
     def from_checkpoint(cls, ckpt_path: str, config_path: str, device: str = "cuda", precision: str = "fp32"):
+        """Checkpoint adapter of extract_indices.py:309-323: strict load first, then the reference's non-strict
+        fallback -- which here still has to match at least one tensor per module (a model that silently keeps its
+        random initialisation is never what the caller asked for)."""
         cfg = configs.load_model_yaml(config_path)
         ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
-        sd = ckpt.get("state_dict", ckpt.get("model", ckpt)) if isinstance(ckpt, dict) else ckpt
-        enc = _strip_prefix(sd, "encoder.") or _strip_prefix(sd, "model.CodecEnc.")
-        dec = _strip_prefix(sd, "decoder.") or _strip_prefix(sd, "model.generator.")
+        enc, dec, other = cls.split_checkpoint(ckpt)
         m = cls(cfg, device=device, precision=precision)
         try:
             m.encoder.load_state_dict(enc, strict=True)
             m.decoder.load_state_dict(dec, strict=True)
+            print(f"State dict loaded strictly ({len(enc)} encoder + {len(dec)} decoder tensors"
+                  + (f", {other} entries of other modules ignored" if other else "") + ").")
         except RuntimeError as e:  # the reference falls back to non-strict loading (extract_indices.py:318-323)
             print(f"Strict state_dict loading failed: {e}. Attempting non-strict loading.")
-            m.encoder.load_state_dict(enc, strict=False)
-            m.decoder.load_state_dict(dec, strict=False)
+            for name, mod, part in (("encoder", m.encoder, enc), ("decoder", m.decoder, dec)):
+                own = mod.state_dict()
+                usable = {k: v for k, v in part.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+                if not usable:
+                    raise RuntimeError(f"non-strict loading matched no {name} tensor: wrong config for this checkpoint?") from e
+                res = mod.load_state_dict(usable, strict=False)
+                skipped = sorted(set(part) - set(usable))
+                print(f"  {name}: loaded {len(usable)} tensors, {len(res.missing_keys)} missing (keep their initial values), "
+                      f"{len(skipped)} unexpected / mis-shaped skipped")
         return m
 
     # -- reference call pattern ---------------------------------------------------------------

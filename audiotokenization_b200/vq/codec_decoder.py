@@ -13,7 +13,7 @@ from torch import nn
 from .. import ops
 from . import activations
 from .alias_free_torch import Activation1d
-from .module import DecoderBlock, ResLSTM, WNConv1d
+from .module import DecoderBlock, ResLSTM, WNConv1d, module_scope
 from .residual_vq import ResidualVQ
 
 
@@ -50,19 +50,21 @@ class BigCodecDecoder(nn.Module):
             nn.Tanh(),
         ]
         self.model = nn.Sequential(*layers)
+        self.precision = None     # arithmetic mode of this module's own calls (None: the enclosing precision_scope)
         self.eval()
 
     # ---- channels-last cores ----------------------------------------------------
     def decode_cl(self, z_cl):
         """z_cl [B,T',C] -> waveform [B,T,1]."""
         mods = list(self.model)
-        h = mods[0].forward_cl(z_cl)
-        for m in mods[1:-3]:
-            h = m.forward_cl(h)
-        act, conv = mods[-3], mods[-2]
-        if act.antialias:
-            return conv.forward_cl(act.forward_cl(h), tanh=True)
-        return conv.forward_cl(h, act=act.act, tanh=True)
+        with module_scope(self):
+            h = mods[0].forward_cl(z_cl)
+            for m in mods[1:-3]:
+                h = m.forward_cl(h)
+            act, conv = mods[-3], mods[-2]
+            if act.antialias:
+                return conv.forward_cl(act.forward_cl(h), tanh=True)
+            return conv.forward_cl(h, act=act.act, tanh=True)
 
     # ---- reference API ------------------------------------------------------------
     @torch.no_grad()

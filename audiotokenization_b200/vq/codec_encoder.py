@@ -13,7 +13,7 @@ from torch import nn
 from .. import ops
 from . import activations
 from .alias_free_torch import Activation1d
-from .module import EncoderBlock, ResLSTM, WNConv1d, _act_conv
+from .module import EncoderBlock, ResLSTM, WNConv1d, _act_conv, module_scope
 
 
 class BigCodecEncoder(nn.Module):
@@ -38,6 +38,7 @@ class BigCodecEncoder(nn.Module):
         ]
         self.block = nn.Sequential(*block)
         self.enc_dim = d_model
+        self.precision = None     # arithmetic mode of this module's own calls (None: the enclosing precision_scope)
         self.eval()
 
     def _split(self):
@@ -49,9 +50,10 @@ class BigCodecEncoder(nn.Module):
         """Conv stem + EncoderBlocks: x_cl [B,T,1] -> frame-rate features [B,T',enc_dim].  This part is
         independent per utterance AND per time tile, so it is run in small micro-batches."""
         front, _, _, _ = self._split()
-        h = front[0].forward_cl(x_cl)
-        for m in front[1:]:
-            h = m.forward_cl(h)
+        with module_scope(self):
+            h = front[0].forward_cl(x_cl)
+            for m in front[1:]:
+                h = m.forward_cl(h)
         return h
 
     # The deep end of the conv stack has few 128-frame tiles per utterance (94 at 256 channels, 19 after the last
@@ -67,26 +69,29 @@ class BigCodecEncoder(nn.Module):
     def front_shallow_cl(self, x_cl, out=None):
         """Stem + EncoderBlocks up to the ResidualUnits of the second-to-last block; ``out`` = destination slice."""
         stem, whole, pivot, _ = self._front_stages()
-        h = stem.forward_cl(x_cl)
-        for m in whole:
-            h = m.forward_cl(h)
-        return pivot.units_cl(h, out=out)
+        with module_scope(self):
+            h = stem.forward_cl(x_cl)
+            for m in whole:
+                h = m.forward_cl(h)
+            return pivot.units_cl(h, out=out)
 
     def front_deep_cl(self, h):
         """The pivot block's strided conv + the last block -> frame-rate features."""
         _, _, pivot, rest = self._front_stages()
-        h = pivot.down_cl(h)
-        for m in rest:
-            h = m.forward_cl(h)
+        with module_scope(self):
+            h = pivot.down_cl(h)
+            for m in rest:
+                h = m.forward_cl(h)
         return h
 
     def back_cl(self, h):
         """[ResLSTM] + SnakeBeta + final conv on frame-rate features.  The LSTM is sequential in time, so
         it is run over as many utterances at once as possible (its cost per step is almost flat in B)."""
         _, rnn, act, conv = self._split()
-        for m in rnn:
-            h = m.forward_cl(h)
-        return _act_conv(act, conv, h)
+        with module_scope(self):
+            for m in rnn:
+                h = m.forward_cl(h)
+            return _act_conv(act, conv, h)
 
     def forward_cl(self, x_cl):
         """x_cl [B,T,1] -> latents [B,T',out_channels] (channels-last)."""

@@ -69,6 +69,28 @@ class precision_scope:
         return False
 
 
+class module_scope:
+    """Arithmetic mode of a top-level module call: ``BigCodecEncoder`` / ``BigCodecDecoder`` carry their own
+    ``precision`` attribute (set by ``BigCodecModel``), so the reference's call pattern
+    ``lm.model['CodecEnc'](x)`` -- calling the sub-module directly -- runs in the mode the model was built with
+    instead of silently falling back to the process-wide default.  ``None`` keeps the enclosing scope's mode."""
+
+    def __init__(self, module):
+        self.mode = getattr(module, "precision", None)
+        if self.mode is not None and self.mode not in ops.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(ops.PRECISIONS)}")
+
+    def __enter__(self):
+        self.prev = _PRECISION[0]
+        if self.mode is not None:
+            _PRECISION[0] = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        _PRECISION[0] = self.prev
+        return False
+
+
 def _fold(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """weight_norm(dim=0): w = g * v / ||v|| with the norm over all dims but 0 (float64 fold, once per load)."""
     v64, g64 = v.detach().double(), g.detach().double()

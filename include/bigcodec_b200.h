@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BC_ABI_VERSION 3
+#define BC_ABI_VERSION 4
 
 typedef void* bc_stream_t; /* cudaStream_t */
 
@@ -58,6 +58,9 @@ enum {
 
 int bc_abi_version(void);
 const char* bc_last_error(void);
+/* Kernel-selection knobs this process runs with (read from the environment once, at first use), as a
+ * "key=value ..." string: recorded by bench.py next to every number.  None of them changes results. */
+int bc_policy(char* buf, size_t n);
 /* 0 if device `dev` exists and is sm_100; fills optional outputs. */
 int bc_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
 
@@ -174,7 +177,9 @@ int bc_lstm_recurrent_fwd(const float* pre, const float* w_hh_packed, const floa
  * instead of a grid barrier.  w_image = [4H/NS slices][split][H/16][2][NS][8] bf16 with slice row
  * g*(NS/4)+u = W_hh[g*H + slice*(NS/4) + u], NS = bc_lstm_tc_slice_cols(precision).
  * bc_lstm_tc_max_batch: largest B one launch accepts on the current device (0 = no tensor-core plan for
- * this H; use bc_lstm_recurrent_fwd).  Workspace need not be zeroed. */
+ * this H; use bc_lstm_recurrent_fwd).  Workspace need not be zeroed.
+ * Gate non-linearities in these modes use the SFU exponential and the approximate divide (|error| ~2e-7,
+ * below the split-operand error); they saturate to 0 / +-1 for any finite pre-activation or cell state. */
 int bc_lstm_tc_slice_cols(int precision);
 int bc_lstm_tc_max_batch(int H, int precision);
 size_t bc_lstm_tc_workspace_bytes(int B, int H, int precision);

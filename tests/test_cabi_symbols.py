@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/ but not exported"
     assert names == set(_cabi._SIGNATURES), (names ^ set(_cabi._SIGNATURES))
-    assert lib.bc_abi_version() == 3
+    assert lib.bc_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

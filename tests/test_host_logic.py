@@ -277,3 +277,83 @@ def test_front_pipeline_flushes_when_the_clip_length_changes():
     fb = pipe.take()
     assert fa.shape == (2, 5, 1) and fb.shape == (3, 3, 1)
     assert enc.deep_batches == [2, 3]
+
+
+@pytest.mark.parametrize("fmt", ["state_dict", "model", "bare", "codecenc", "module_prefixed"])
+def test_from_checkpoint_accepts_the_reference_checkpoint_formats(tmp_path, fmt):
+    """extract_indices.py:309-323: ``{'state_dict'}`` (Lightning: encoder.* / decoder.* next to discriminator
+    entries), ``{'model'}``, a bare state dict; the wrappers' ``model.CodecEnc`` / ``model.generator`` names."""
+    import yaml
+    from audiotokenization_b200.model import BigCodecModel
+    cfg = configs.get_config("tiny")
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=3)
+    pe, pd = {"codecenc": ("model.CodecEnc.", "model.generator."), "module_prefixed": ("module.encoder.", "module.decoder.")}.get(
+        fmt, ("encoder.", "decoder."))
+    sd = {pe + k: v for k, v in enc_sd.items()}
+    sd.update({pd + k: v for k, v in dec_sd.items()})
+    sd["discriminator.mpd.0.weight"] = torch.zeros(3)                       # other modules of the Lightning checkpoint
+    ckpt = {"state_dict": sd, "epoch": 3} if fmt in ("state_dict", "codecenc", "module_prefixed") else ({"model": sd} if fmt == "model" else sd)
+    torch.save(ckpt, tmp_path / "last.ckpt")
+    with open(tmp_path / "config.yaml", "w") as f:
+        yaml.safe_dump({"model": {"codec_encoder": dict(cfg["codec_encoder"], type="bigcodec"),
+                                  "codec_decoder": dict(cfg["codec_decoder"], vq_dim=8)}}, f)
+    m = BigCodecModel.from_checkpoint(str(tmp_path / "last.ckpt"), str(tmp_path / "config.yaml"), device="cpu", precision="bf16x3")
+    for k, v in enc_sd.items():
+        assert torch.equal(m.encoder.state_dict()[k], v), k
+    for k, v in dec_sd.items():
+        assert torch.equal(m.decoder.state_dict()[k], v), k
+    assert m.precision == "bf16x3" and m.encoder.precision == "bf16x3" and m.decoder.precision == "bf16x3"
+
+
+def test_from_checkpoint_non_strict_fallback_and_refusal(tmp_path, capsys):
+    import yaml
+    from audiotokenization_b200.model import BigCodecModel
+    cfg = configs.get_config("tiny")
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=4)
+    with open(tmp_path / "config.yaml", "w") as f:
+        yaml.safe_dump({"codec_encoder": cfg["codec_encoder"], "codec_decoder": cfg["codec_decoder"]}, f)
+    # one tensor missing, one unexpected: strict fails, the reference's non-strict fallback loads the rest
+    sd = {"encoder." + k: v for k, v in enc_sd.items()}
+    sd.update({"decoder." + k: v for k, v in dec_sd.items()})
+    dropped = next(k for k in sd if k.endswith("bias"))
+    del sd[dropped]
+    sd["decoder.extra.weight"] = torch.zeros(2)
+    torch.save({"state_dict": sd}, tmp_path / "partial.ckpt")
+    m = BigCodecModel.from_checkpoint(str(tmp_path / "partial.ckpt"), str(tmp_path / "config.yaml"), device="cpu")
+    out = capsys.readouterr().out
+    assert "Strict state_dict loading failed" in out and "1 missing" in out
+    k0 = next(k for k in enc_sd if k.endswith("weight_v"))
+    assert torch.equal(m.encoder.state_dict()[k0], enc_sd[k0])
+    # nothing under a known prefix: an error, never a silently random-initialised model
+    torch.save({"state_dict": {"foo." + k: v for k, v in enc_sd.items()}}, tmp_path / "alien.ckpt")
+    with pytest.raises(ValueError, match="no encoder/decoder entries"):
+        BigCodecModel.from_checkpoint(str(tmp_path / "alien.ckpt"), str(tmp_path / "config.yaml"), device="cpu")
+    # right prefixes, wrong architecture: non-strict loading matches nothing -> refuse
+    big = configs.get_config("debug")
+    e2, d2 = synth.make_state_dicts(big, seed=1)
+    sd2 = {"encoder." + k: v + 0 for k, v in e2.items() if v.dim() == 3}
+    sd2.update({"decoder." + k: v for k, v in d2.items() if v.dim() == 3})
+    torch.save(sd2, tmp_path / "wrong.ckpt")
+    with pytest.raises(RuntimeError, match="matched no"):
+        BigCodecModel.from_checkpoint(str(tmp_path / "wrong.ckpt"), str(tmp_path / "config.yaml"), device="cpu")
+
+
+def test_precision_lives_on_the_modules_not_only_in_the_process_global():
+    """``BigCodecModel(precision='bf16x3').encoder(x)`` (the reference's ``lm.model['CodecEnc'](x)`` call
+    pattern) must run in the model's mode.  Checked on CPU through the mode the leaf ops would see."""
+    from audiotokenization_b200.model import BigCodecModel
+    cfg = configs.get_config("tiny")
+    m = BigCodecModel(cfg, device="cpu", precision="bf16x3")
+    assert M.get_precision() == "fp32"
+    seen = []
+    with M.module_scope(m.encoder):
+        seen.append(M.get_precision())
+    assert seen == ["bf16x3"] and M.get_precision() == "fp32"
+    m.precision = "bf16"
+    with M.module_scope(m.decoder):
+        assert M.get_precision() == "bf16"
+    plain = BigCodecEncoder(**cfg["codec_encoder"])
+    with M.precision_scope("bf16x3"), M.module_scope(plain):                # no own mode: the enclosing scope's
+        assert M.get_precision() == "bf16x3"
+    with pytest.raises(ValueError):
+        m.precision = "fp8"

@@ -114,3 +114,38 @@ def test_extract_to_directory_groups_equal_lengths_writes_layout_and_counts_erro
         assert a.dtype == np.int16 and a[:, 0].tolist() == [400, i, 0]
     assert np.load(os.path.join(str(tmp_path), "dev", "8", "1", "8_1_y.npy"))[:, 0].tolist() == [600, 50, 0]
     assert not os.path.exists(os.path.join(str(tmp_path), "dev", "9", "9", "9-9-z.npy"))
+
+
+def test_extract_to_directory_bounds_its_buffer_and_retries_failed_groups_one_by_one(tmp_path):
+    """Full-length files: every length unique.  The buffer must not grow with the corpus, and a group that fails is
+    retried per utterance so that one bad utterance costs one error (extract_indices.py:565-574)."""
+    items = ((torch.full((300 + i,), 0.01), "dev", f"1-{i}-u") for i in range(40))       # a generator: nothing is pre-loaded
+    model = _FakeModel()
+    seen_max = [0]
+    orig = model.extract_indices
+
+    def spy(host, **kw):
+        seen_max[0] = max(seen_max[0], len(model.calls))
+        return orig(host, **kw)
+
+    model.extract_indices = spy
+    saved, errors = extract.extract_to_directory(model, items, str(tmp_path), group_size=8, writers=2, verbose=False,
+                                                 max_buffered_items=5)
+    assert (saved, errors) == (40, 0)
+    assert len(model.calls) == 40 and all(n == 1 for n, _ in model.calls)
+    # with a cap of 5 waiting utterances the first encode happens after 6 items, not after the whole corpus
+    assert model.calls[0][1] in range(300, 306)
+
+    class _FailsInGroups(_FakeModel):
+        def extract_indices(self, host, micro_batch=8, rnn_batch=256):
+            if host.shape[0] > 1 or float(host[0, 0, 0]) > 0.9:          # any group fails; alone only the bad one does
+                self.calls.append(tuple(host.shape[::2]))
+                raise RuntimeError("boom")
+            return super().extract_indices(host, micro_batch, rnn_batch)
+
+    items = [(torch.full((500,), 1.0 if i == 2 else 0.1), "dev", f"2-{i}-v") for i in range(4)]
+    model = _FailsInGroups()
+    saved, errors = extract.extract_to_directory(model, items, str(tmp_path), group_size=4, writers=1, verbose=False)
+    assert (saved, errors) == (3, 1)
+    assert not os.path.exists(os.path.join(str(tmp_path), "dev", "2", "2", "2-2-v.npy"))
+    assert os.path.exists(os.path.join(str(tmp_path), "dev", "2", "3", "2-3-v.npy"))
