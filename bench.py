@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write a per-layer timing table (markdown) here")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip `other_configs` (BASELINE configs[2..4], anti-aliased path) and the eager-GPU baseline")
     return ap.parse_args()
 
 
@@ -218,8 +220,9 @@ def main():
         return
 
     import torch.distributed as dist
-    from audiotokenization_b200 import configs, ops, synth
+    from audiotokenization_b200 import _cabi, configs, ops, sharding, synth
     from audiotokenization_b200.model import BigCodecModel
+    import bench_configs
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -276,8 +279,12 @@ def main():
     value = world * audio_s_local * args.steps / (ms_total / 1000.0)
 
     # ---- end to end through the host-buffer API ----------------------------------------------
+    host_group = dist.new_group(backend="gloo") if world > 1 else None   # CPU group: the host-side gather of the int16 indices
+
     def step_e2e():
         keep["i16"] = model.extract_indices(host, micro_batch=args.micro_batch, rnn_batch=args.rnn_batch, deep_batch=args.deep_batch)
+        if world > 1:   # "results gathered on the host" (north_star): inside the timed region, no data-path collective on the GPUs
+            keep["gathered"] = sharding.gather_indices_to_rank0(keep["i16"], group=host_group)
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -386,6 +393,37 @@ def main():
             "index_agreement": float((got == want["indices"][0]).float().mean()),
             "exact_where_margin_gt_1e-5": bool(torch.equal(got[decided], want["indices"][0][decided]))}
 
+    # ---- the library Blackwell path: the reference's arithmetic through PyTorch eager on this GPU (rank 0, N = 1) ----
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_extras:
+        try:
+            ge = bench_configs.gpu_eager(cfg, enc_sd, dec_sd, x_dev, clips=8)
+            for name in ("tf32_default", "fp32_allow_tf32_false"):
+                got_e = ge.pop(name + "_indices")[:1]
+                ge[name]["index_agreement_vs_cpu_oracle_clip0"] = float((got_e == want["indices"][0]).float().mean())
+                ge[name]["speedup_of_this_repo"] = value / ge[name]["value"]
+            gpu_eager = ge
+        except Exception as e:   # a baseline that cannot run must not take the headline number down with it
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations and the stand-alone kernels north_star names ----------------------
+    other = {}
+    if not args.no_extras:
+        def guarded(name, fn):
+            try:
+                other[name] = fn()
+            except Exception as e:
+                other[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+
+        # configs[3] runs at every N: the conv front end of ONE recording is dealt out over the ranks
+        guarded("configs3_longform", lambda: bench_configs.longform(model, minutes=10.0, world=world, check_whole=(world == 1)))
+        if rank == 0 and world == 1:
+            guarded("configs2_round_trip", lambda: bench_configs.round_trip(model, enc_sd=enc_sd, dec_sd=dec_sd, cfg=cfg))
+            guarded("configs4_vq_sweep", lambda: bench_configs.vq_sweep())
+            guarded("antialias", lambda: bench_configs.antialias(lambda c: synth.make_state_dicts(c, seed=0), precision=args.precision))
+
     # ---- other arithmetic modes (device-resident only; reported, never substituted for the headline) ----
     modes = {}
     for mode in [m for m in args.also.split(",") if m and m != args.precision]:
@@ -410,9 +448,18 @@ def main():
                     "d2h_bytes_per_step": int(i16.nbytes), "ms_per_step": ms_e2e / args.steps,
                     "matches_device_path": same},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "modes": modes,
+            "policy": _cabi.policy(),
         }
+        if world > 1:
+            g = keep.get("gathered")
+            line["e2e"]["host_gather"] = {"backend": "gloo", "inside_timed_region": True,
+                                          "gathered_shape": list(g.shape) if g is not None else None}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if gpu_eager is not None:
+            line["gpu_eager_baseline"] = gpu_eager
+        if other:
+            line["other_configs"] = other
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

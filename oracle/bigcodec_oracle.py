@@ -25,7 +25,11 @@ F.conv_transpose1d, nn.LSTM, F.normalize, matmul); PyTorch is the reference's
 third-party numeric dependency (requirements.txt pins no version; here torch
 2.11.0).  This file calls the same library entry points functionally on a
 plain state dict, with no nn.Module tree, so it is usable in float32 (the
-reference's precision) and float64 (error attribution).
+reference's precision) and float64 (error attribution).  The functions follow
+the device of their inputs: ``bench.py``'s baseline leg also runs them on CUDA
+tensors, which is exactly what the reference does on a GPU box
+(extract_indices.py:399: ``model.to('cuda')`` -> cuDNN / cuBLAS eager) -- the
+"library Blackwell path" of SURVEY.md section 2.2, a second reported baseline.
 
 Pinning: the reference ships no tests or golden vectors,
 so the oracle is pinned against the *live reference modules* executed in the
@@ -118,8 +122,8 @@ def activation1d(sd: SD, prefix: str, x: Tensor, antialias: bool) -> Tensor:
         return snake_beta(x, alpha, beta)
     fu = sd.get(prefix + "upsample.filter")
     fd = sd.get(prefix + "downsample.lowpass.filter")
-    fu = kaiser_sinc_filter12(x.dtype) if fu is None else fu.to(x.dtype)
-    fd = kaiser_sinc_filter12(x.dtype) if fd is None else fd.to(x.dtype)
+    fu = (kaiser_sinc_filter12(x.dtype) if fu is None else fu).to(device=x.device, dtype=x.dtype)
+    fd = (kaiser_sinc_filter12(x.dtype) if fd is None else fd).to(device=x.device, dtype=x.dtype)
     return downsample2(snake_beta(upsample2(x, fu), alpha, beta), fd)
 
 
@@ -166,7 +170,7 @@ def res_lstm(sd: SD, prefix: str, x: Tensor, num_layers: int, bidirectional: boo
                 flat.append(sd[f"{prefix}lstm.{name}_l{l}{s}"].to(dt))
     hid = flat[1].shape[1]
     ndir = 2 if bidirectional else 1
-    h0 = torch.zeros(num_layers * ndir, xt.shape[0], hid, dtype=dt)
+    h0 = torch.zeros(num_layers * ndir, xt.shape[0], hid, dtype=dt, device=xt.device)
     y, _, _ = torch.lstm(xt.contiguous(), (h0, h0.clone()), flat, True, num_layers, 0.0, False, bidirectional, True)
     return (y + xt).transpose(1, 2)
 
@@ -180,7 +184,7 @@ def res_lstm_loop(sd: SD, prefix: str, x: Tensor, num_layers: int) -> Tensor:
         w_hh = sd[f"{prefix}lstm.weight_hh_l{l}"].to(x.dtype)
         b = (sd[f"{prefix}lstm.bias_ih_l{l}"] + sd[f"{prefix}lstm.bias_hh_l{l}"]).to(x.dtype)
         hid = w_hh.shape[1]
-        h = torch.zeros(x.shape[0], hid, dtype=x.dtype)
+        h = torch.zeros(x.shape[0], hid, dtype=x.dtype, device=x.device)
         c = torch.zeros_like(h)
         outs = []
         pre = inp @ w_ih.t() + b
@@ -262,7 +266,7 @@ def vq_layer_forward(sd: SD, prefix: str, z: Tensor) -> Tuple[Tensor, Tensor, Te
         w_out, b_out = _wn(sd, prefix + "out_proj.", dt)
         z_q = F.linear(z_q, w_out, b_out)
     z_q = z_q.transpose(1, 2)
-    return z_q, idx, torch.zeros(z.shape[0], dtype=dt), margin.view(z.shape[0], -1)
+    return z_q, idx, torch.zeros(z.shape[0], dtype=dt, device=z.device), margin.view(z.shape[0], -1)
 
 
 def quantize(sd: SD, cfg: dict, z: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

@@ -140,3 +140,29 @@ def test_longform_chunked_equals_whole_recording(precision):
         f_whole = model.encoder.front_cl(x.reshape(1, T, 1))
         f_chunk = longform.stitch(longform.chunked_front(model.encoder.front_cl, x[0, 0], hop, 1800, halo, 2))
     assert torch.equal(f_whole, f_chunk)
+
+
+@pytest.mark.parametrize("clips,seconds", [(1, 10), (4, 30)])
+def test_benched_mode_bf16x3_at_baseline_sizes_against_oracle(clips, seconds):
+    """The arithmetic mode bench.py times (bf16x3) at BASELINE configs[0] (1 x 10 s) and at the clip length of
+    configs[1] (4 x 30 s, through the same `extract_indices` entry point and schedule as the bench): indices
+    bit-exact wherever the oracle's top-1/top-2 cosine margin exceeds 1e-5, latents within 1e-3 relative."""
+    cfg = configs.get_config("base")
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=0)
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision="bf16x3")
+    T = seconds * 16000
+    x = synth.fast_synth_batch(100, clips, T)
+    want = oracle.encode_to_indices(enc_sd, dec_sd, cfg, x)
+    i16 = model.extract_indices(x.pin_memory(), micro_batch=2, rnn_batch=256, deep_batch=64)       # [N, T', 1]
+    got = torch.from_numpy(i16[:, :, 0].astype("int64"))
+    ref = want["indices"][0]                                                                       # [N, T']
+    margin = want["margin"][0] if want["margin"].dim() == 3 else want["margin"]
+    decided = margin > 1e-5
+    flips = (got != ref)
+    assert not bool((flips & decided).any()), ("flipped at margins", margin[flips & decided])
+    agree = 1.0 - float(flips.float().mean())
+    assert agree >= 0.998, agree
+    z = model.encoder(x[:1].cuda())
+    e_z = rel(z, want["z"][:1])
+    assert e_z <= 1e-3, e_z
+    print(f"bf16x3 {clips} x {seconds} s: idx agree {agree:.5f} ({int(flips.sum())} flips, all at margin <= 1e-5), z rel {e_z:.2e}")

@@ -63,22 +63,33 @@ def test_round_trip_matches_reference_fixture(case):
 
 @pytest.mark.parametrize("case", ["base_1s", "debug_1s", "config9_base_1s", "debug_causal_1s", "tiny", "base_aa_1s", "default_half_s"])
 def test_tensor_core_split_mode_meets_the_fp32_contract(case):
-    """bf16x3 (tcgen05, hi/lo split operands, fused ResidualUnits, tensor-core LSTM): latents and waveforms
-    within 1e-3 of the reference (asserted 5x tighter), indices bit-exact where the margin exceeds 1e-5...
-    end to end through ~60 layers a 1e-5-class latent error can still flip a frame whose margin is below
-    ~1e-4, so exactness is asserted for margin > 2e-4 and the agreement rate is reported."""
+    """bf16x3 (tcgen05, hi/lo split operands, fused ResidualUnits, tensor-core LSTM) -- the mode bench.py times --
+    against the reference fixtures at the contract's own thresholds: indices bit-exact wherever the top-1/top-2
+    cosine margin exceeds 1e-5, latents and waveforms within 1e-3 relative (asserted 5x tighter: 2e-4).  The
+    sub-modules are called directly, like the reference's ``lm.model['CodecEnc'](x)``: they run in the model's mode."""
     g = load_golden(case)
     cfg = configs.get_config(g["cfg_name"], antialias=g["antialias"])
     enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=g["seed"])
     model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision="bf16x3")
     x = synth.synth_batch(0, g["batch"], g["num_samples"], g["kind"]).cuda()
     out = model(x, round_trip=True)
-    z = model.encoder(x)
+    from audiotokenization_b200 import ops
+    n0 = ops.STATS["launches"]
+    prof, ops.PROFILE = ops.PROFILE, []
+    try:
+        z = model.encoder(x)                              # direct sub-module call: must be the tensor-core path
+        kernels = {rec[4] for rec in ops.PROFILE}
+    finally:
+        ops.PROFILE = prof
+    assert ops.STATS["launches"] > n0
+    if cfg["codec_encoder"]["ngf"] >= 16 and not g["antialias"]:
+        assert kernels & {"conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "conv1d_tc_kernel"}, kernels
     e_z = rel(z.cpu().numpy(), g["z_f64"])
     assert e_z <= 2e-4, e_z
     idx = out["indices"].cpu().numpy()
-    decided = g["margin_f64"][None] > 2e-4
-    assert np.array_equal(idx[decided], g["idx_f64"][decided])
+    decided = g["margin_f64"][None] > 1e-5
+    assert np.array_equal(idx[decided], g["idx_f64"][decided]), (
+        "flipped frames at margins", g["margin_f64"][None][decided & (idx != g["idx_f64"])])
     agree = float((idx == g["idx_f32"]).mean())
     assert agree >= 0.99, agree
     y = model.decoder(torch.from_numpy(g["zq_f32"]).cuda(), vq=False)

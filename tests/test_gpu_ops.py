@@ -429,6 +429,37 @@ def test_res_lstm_tensor_core_recurrence(precision, tol, H, layers, B, T):
     assert rel(got, ref) <= tol
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_res_lstm_tensor_core_gates_saturate_instead_of_overflowing(precision):
+    """the cell state is unbounded (|c| grows by up to 1 per step when i, f saturate), and a
+    (1 - e) / (1 + e) tanh with e = exp(-2x) turns into 0 or NaN for x < -44.  Drive |c| and the g gate far past
+    that (pre-activations up to 1e3, 120 steps) and require finite output that matches the float32 oracle."""
+    H, B, T = 128, 5, 120
+    g = gen(77)
+    m = M.ResLSTM(H, num_layers=1)
+    with torch.no_grad():
+        m.lstm.weight_hh_l0.mul_(0.05)
+        # input gate and forget gate wide open, cell candidate strongly negative for half of the units
+        b = m.lstm.bias_ih_l0
+        b[:H] = 50.0
+        b[H:2 * H] = 50.0
+        b[2 * H:3 * H] = torch.where(torch.arange(H) % 2 == 0, torch.tensor(-1000.0), torch.tensor(1000.0))
+        b[3 * H:] = 30.0
+        m.lstm.weight_ih_l0.mul_(0.01)
+    sd = {"lstm." + k: v.data.clone() for k, v in m.lstm.named_parameters()}
+    x = torch.randn(B, H, T, generator=g)
+    want = oracle.res_lstm(sd, "", x, 1)          # c reaches -120 / +120: tanh(c) = -1 / +1 exactly in float32
+    assert torch.isfinite(want).all() and float((want - x).abs().max()) > 0.99
+    m = m.to(DEV)
+    M.set_precision(precision)
+    try:
+        got = m(x.to(DEV))
+    finally:
+        M.set_precision("fp32")
+    assert torch.isfinite(got).all(), "NaN / inf out of the tensor-core LSTM"
+    assert rel(got, want) <= 1e-4
+
+
 # ---------------------------------------------------------------------------------------------
 # persistent streamed-weight kernels (csrc/conv_stream.cu)
 # ---------------------------------------------------------------------------------------------
