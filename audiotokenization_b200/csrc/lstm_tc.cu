@@ -2,18 +2,30 @@
 //
 //   G_t[B x 4H] = pre_t + h_{t-1}[B x H] * W_hh^T ,  gates i,f,g,o   (nn.LSTM inside ResLSTM, vq/module.py:143-167)
 //
-// Decomposition.  CTA (m, n) owns 128 batch rows (m) and NS gate columns (n) = U = NS/4 hidden units with
-// all four gates; its W_hh slice [NS x H] (bf16 hi [, lo]) stays resident in shared memory for the whole
-// sequence.  Every time step:
-//   TMA thread   waits until all n-slices of its m-tile have published h_{t-1}, then streams the
-//                bf16 h tile [128 x H] (stored in HBM/L2 directly in the UMMA K-major image) in K chunks
+// Decomposition.  A CTA owns NS gate columns (n) = U = NS/4 hidden units with all four gates -- its W_hh slice
+// [NS x H] (bf16 hi [, lo]) stays resident in shared memory for the whole sequence -- and TPC batch tiles of 128 rows.
+// Every time step, for each of its batch tiles in turn:
+//   TMA thread   waits until the n-slices that own a K chunk of the tile's h_{t-1} have published it, then streams
+//                the bf16 h tile [128 x H] (stored in HBM/L2 directly in the UMMA K-major image) in K chunks
 //                through a shared-memory ring (cp.async.bulk + mbarrier);
-//   MMA thread   H/16 [x3] tcgen05.mma (M=128, N=NS) into one TMEM accumulator, chunk by chunk as they land;
+//   MMA thread   H/16 [x2] tcgen05.mma (M=128) into the tile's TMEM accumulator, chunk by chunk as they land.
+//                Split precision: w_hi and w_lo sit side by side as ONE B operand of 2*NS rows, so a_hi meets both in
+//                a single MMA of width 2*NS (columns [0,NS) = hi*hi, [NS,2NS) = hi*lo) and a_lo * w_hi is a second one
+//                of width NS into columns [0,NS): two A fetches and 48 + 40 tensor cycles per 16 channels instead of
+//                three and 3 x 40 (NS = 32);
 //   16 gate warps  tcgen05.ld their (32 rows x UPW units x 4 gates) patch, add the pre-activation (prefetched
 //                from HBM during the MMA phase), apply the gates with c kept in registers, write y (fp32,
-//                + skip) and publish h_t as bf16 hi[/lo] into the exchange buffer, then bump the m-tile's
+//                + skip) and publish h_t as bf16 hi[/lo] into the exchange buffer, then bump the tile's
 //                step counter (release); no grid-wide barrier -- only the CTAs that share batch rows wait
 //                for each other.
+// TPC = 2 (batches above 256 rows in split precision): the two tiles of a CTA are independent sequences, so while the
+// h_t of one is being published, becoming visible and travelling through L2 (the latency chain that bounds a step:
+// ~8 us, tensor pipe and copy engine mostly idle), the other tile's copies, MMAs and gates run: 11.2 us per step of
+// 512 rows against 2 x 8.0 us for two launches of 256 (B200, H = 512).  Measured and rejected: separate TMA threads,
+// gate-warp halves and a tagged, shared ring per tile (13.2 us: eight gate warps per tile double the gate phase that
+// sits on each tile's chain, and the ring is still only two 64 KB slots deep); 64-channel chunks (12.5 us at 256 rows:
+// the per-chunk barrier waits and commits of the MMA thread cost more than the finer pipelining gains); one 16-byte
+// poll of four chunk counters (neutral).
 // The kernel is launched cooperatively (all CTAs must be co-resident because they wait on each other).
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -21,26 +33,27 @@
 namespace {
 using namespace bc::tc;
 
-constexpr int LM = 128;         // batch rows per CTA
+constexpr int LM = 128;         // batch rows per tile
 constexpr int KC = 128;         // K elements per streamed chunk
 constexpr int GATE_WARPS = 16;
 constexpr int CNT_STRIDE = 16;  // counters per batch tile (>= H / KC)
 constexpr int L_THREADS = (4 + GATE_WARPS) * 32;   // warp 0: TMA, warp 1: MMA, warps 2-3 idle, warps 4-19: gates
+constexpr int MAX_TPC = 2;
 
 struct LstmTcParams {
   const float* pre;        // [B][T][4H]
-  const uint4* wimg;       // [n_slices][split][H/16][2][NS][8] bf16
+  const uint4* wimg;       // [n_slices][H/16][2][split*NS][8] bf16 (rows: hi slice, then lo slice)
   const float* skip;       // [B][T][H] or NULL
   float* y;                // [B][T][H]
   __nv_bfloat16* hx;       // [2][m_tiles][split][H/8][128][8]
   unsigned int* counters;  // [m_tiles][CNT_STRIDE]: one step counter per (batch tile, K chunk of h)
-  int B, T, H, NS, nslot, n_slices;
-  uint32_t idesc;
+  int B, T, H, NS, nslot, n_slices, m_tiles;
+  uint32_t idesc_wide, idesc_ns;   // N = split*NS (a_hi x [w_hi | w_lo]) and N = NS (a_lo x w_hi)
   long long* trace;   // debug: [step < 64][8] clock64 stamps of CTA (0,0), steps 100.. (NULL = off)
 };
 
 #ifdef BC_TRACE
-#define LTRACE(ev) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t >= 100 && t < 164) p.trace[(t - 100) * 8 + (ev)] = clock64(); } while (0)
+#define LTRACE(ev) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && j == 0 && t >= 100 && t < 164) p.trace[(t - 100) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define LTRACE(ev) do { } while (0)
 #endif
@@ -56,42 +69,50 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 
-template <int SPLIT, int UPW>
+template <int SPLIT, int UPW, int TPC>
 __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, NS = p.NS, U = NS / 4;
   const int nchunks = H / KC;
-  const int n = blockIdx.x, m = blockIdx.y;
-  const uint32_t w_split = (uint32_t)NS * H * 2u;
+  const int n = blockIdx.x;
+  // batch tiles of this CTA: blockIdx.y, blockIdx.y + gridDim.y (the second one may not exist)
+  int ntile = 0;
+#pragma unroll
+  for (int j = 0; j < TPC; ++j) ntile += ((int)blockIdx.y + j * (int)gridDim.y) < p.m_tiles ? 1 : 0;
+  const uint32_t w_bytes = (uint32_t)SPLIT * NS * H * 2u;
   const uint32_t chunk_split = (uint32_t)LM * KC * 2u;           // one chunk of the h tile, one split: 32 KB
   const uint32_t slot_bytes = chunk_split * SPLIT;
+  const uint32_t acc_cols = (uint32_t)SPLIT * NS;                // TMEM columns of one tile's accumulator
   uint8_t* sW = smem_raw;
-  uint8_t* sA = sW + w_split * SPLIT;
+  uint8_t* sA = sW + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)slot_bytes * p.nslot);
-  // bars: full[nslot] | empty[nslot] | acc_full | acc_empty | w_full
+  // bars: full[nslot] | empty[nslot] | acc_full[MAX_TPC] | acc_empty[MAX_TPC] | w_full
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8u * p.nslot, bar_accf = bar0 + 16u * p.nslot,
-                 bar_acce = bar_accf + 8u, bar_w = bar_accf + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslot + 3);
+                 bar_acce = bar_accf + 8u * MAX_TPC, bar_w = bar_acce + 8u * MAX_TPC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslot + 2 * MAX_TPC + 1);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < acc_cols * TPC) tmem_cols <<= 1;
 
   if (tid == 0) {
     for (int s = 0; s < p.nslot; ++s) {
       mbar_init(bar_full + 8u * s, 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
-    mbar_init(bar_accf, 1);
-    mbar_init(bar_acce, GATE_WARPS);
+    for (int j = 0; j < MAX_TPC; ++j) {
+      mbar_init(bar_accf + 8u * j, 1);
+      mbar_init(bar_acce + 8u * j, GATE_WARPS);
+    }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t wbytes = w_split * SPLIT;
-    mbar_expect_tx(bar_w, wbytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)n * wbytes;
-    for (uint32_t off = 0; off < wbytes; off += 32768u)
-      bulk_g2s_notx(smem_u32(sW) + off, src + off, min(32768u, wbytes - off), bar_w);
+    mbar_expect_tx(bar_w, w_bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + (size_t)n * w_bytes;
+    for (uint32_t off = 0; off < w_bytes; off += 32768u)
+      bulk_g2s_notx(smem_u32(sW) + off, src + off, min(32768u, w_bytes - off), bar_w);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NS < 32 ? 32 : NS)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -100,38 +121,43 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   const uint32_t tmem_base = *tmem_slot;
 
   const size_t hx_tile = (size_t)SPLIT * (H / 8) * LM * 8;        // bf16 elements of one m-tile image (all splits)
-  const size_t hx_parity = hx_tile * gridDim.y;
+  const size_t hx_parity = hx_tile * p.m_tiles;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       uint32_t cc = 0;
       for (int t = 0; t < p.T; ++t) {
-        // K chunk c of h_{t-1} is written by the KC/U n-slices that own its hidden units: each chunk is fetched as soon
-        // as ITS producers have published (per-chunk step counters), so the copies and MMAs of the early chunks overlap
-        // the stragglers of the later ones instead of waiting for the slowest of all n-slices
-        const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
-        for (int c = 0; c < nchunks; ++c, ++cc) {
-          if (t > 0) {
-            const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
-            unsigned int seen;
-            unsigned int spins = 0;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + m * CNT_STRIDE + c) : "memory");
-              if (++spins > (1u << 26)) __trap();
-            } while (seen < target);
-            asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
-          }
-          if (c == 0) LTRACE(0);
-          const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
-          mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
-          mbar_expect_tx(bar_full + 8u * slot, slot_bytes);
 #pragma unroll
-          for (int sp = 0; sp < SPLIT; ++sp)
-            bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
-                          src + (size_t)sp * (H / 8) * LM * 8 + (size_t)c * (KC / 8) * LM * 8, chunk_split, bar_full + 8u * slot);
+        for (int j = 0; j < TPC; ++j) {
+          if (j >= ntile) break;
+          const int m = (int)blockIdx.y + j * (int)gridDim.y;
+          // K chunk c of h_{t-1} is written by the KC/U n-slices that own its hidden units: each chunk is fetched as soon
+          // as ITS producers have published (per-chunk step counters), so the copies and MMAs of the early chunks overlap
+          // the stragglers of the later ones instead of waiting for the slowest of all n-slices
+          const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
+          for (int c = 0; c < nchunks; ++c, ++cc) {
+            if (t > 0) {
+              const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
+              unsigned int seen;
+              unsigned int spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + m * CNT_STRIDE + c) : "memory");
+                if (++spins > (1u << 26)) __trap();
+              } while (seen < target);
+              asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
+            }
+            if (c == 0) LTRACE(0);
+            const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
+            mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
+            mbar_expect_tx(bar_full + 8u * slot, slot_bytes);
+#pragma unroll
+            for (int sp = 0; sp < SPLIT; ++sp)
+              bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
+                            src + (size_t)sp * (H / 8) * LM * 8 + (size_t)c * (KC / 8) * LM * 8, chunk_split, bar_full + 8u * slot);
+          }
+          LTRACE(1);
         }
-        LTRACE(1);
       }
     }
   } else if (warp == 1) {
@@ -140,33 +166,36 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
       mbar_wait(bar_w, 0);
       const uint32_t a_plane = LM * 16u;
       const uint32_t hi_d = desc_hi(128u);
-      const uint32_t w_lo0 = desc_lo(smem_u32(sW), (uint32_t)NS * 16u);
+      const uint32_t b_plane = acc_cols * 16u;                      // stride between the two k-planes of a 16-channel group
+      const uint32_t w_lo0 = desc_lo(smem_u32(sW), b_plane);
       uint32_t cc = 0;
       for (int t = 0; t < p.T; ++t) {
-        mbar_wait(bar_acce, ((uint32_t)t & 1u) ^ 1u);   // gate warps have drained the accumulator of step t-1
-        tc_fence_after();
-        for (int c = 0; c < nchunks; ++c, ++cc) {
-          const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
-          mbar_wait(bar_full + 8u * slot, use & 1u);
-          tc_fence_after();
-          uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes, a_plane);
-          uint32_t b_lo = w_lo0 + (((uint32_t)c * (KC / 16) * NS * 32u) >> 4);
-          const uint32_t a_g = (2u * a_plane) >> 4, b_g = ((uint32_t)NS * 32u) >> 4;
 #pragma unroll
-          for (int g = 0; g < KC / 16; ++g, a_lo += a_g, b_lo += b_g) {
-            if (g == 0 && c == 0) mma_bf16_lohi<false>(tmem_base, a_lo, b_lo, hi_d, hi_d, p.idesc);
-            else                  mma_bf16_lohi<true>(tmem_base, a_lo, b_lo, hi_d, hi_d, p.idesc);
-            if (SPLIT == 2) {
-              mma_bf16_lohi<true>(tmem_base, a_lo, b_lo + (w_split >> 4), hi_d, hi_d, p.idesc);
-              mma_bf16_lohi<true>(tmem_base, a_lo + (chunk_split >> 4), b_lo, hi_d, hi_d, p.idesc);
+        for (int j = 0; j < TPC; ++j) {
+          if (j >= ntile) break;
+          mbar_wait(bar_acce + 8u * j, ((uint32_t)t & 1u) ^ 1u);   // gate warps have drained this tile's accumulator of step t-1
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)j * acc_cols;
+          for (int c = 0; c < nchunks; ++c, ++cc) {
+            const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
+            mbar_wait(bar_full + 8u * slot, use & 1u);
+            tc_fence_after();
+            uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes, a_plane);
+            uint32_t b_lo = w_lo0 + (((uint32_t)c * (KC / 16) * 2u * b_plane) >> 4);
+            const uint32_t a_g = (2u * a_plane) >> 4, b_g = (2u * b_plane) >> 4;
+#pragma unroll
+            for (int g = 0; g < KC / 16; ++g, a_lo += a_g, b_lo += b_g) {
+              if (g == 0 && c == 0) mma_bf16_lohi<false>(d, a_lo, b_lo, hi_d, hi_d, p.idesc_wide);
+              else                  mma_bf16_lohi<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc_wide);
+              if (SPLIT == 2) mma_bf16_lohi<true>(d, a_lo + (chunk_split >> 4), b_lo, hi_d, hi_d, p.idesc_ns);   // a_lo * w_hi
             }
+            if (elect_one()) umma_commit(bar_empty + 8u * slot);
+            __syncwarp();
           }
-          if (elect_one()) umma_commit(bar_empty + 8u * slot);
+          if (elect_one()) umma_commit(bar_accf + 8u * j);
           __syncwarp();
+          if (lane == 0) LTRACE(2);
         }
-        if (elect_one()) umma_commit(bar_accf);
-        __syncwarp();
-        if (lane == 0) LTRACE(2);
       }
     }
   } else if (warp >= 4) {
@@ -175,111 +204,133 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
     const int q = warp & 3;                 // TMEM lane quarter
     const int ug = gw >> 2;                 // unit group within the slice
     const int row = q * 32 + lane;          // row within the m-tile
-    const int b = m * LM + row;
-    const bool row_ok = b < p.B;
     const int u_loc = ug * UPW;             // first unit (within the slice) of this thread
     const int u_glb = n * U + u_loc;        // first hidden unit (global index)
-    float c_state[UPW];
+    float c_state[TPC][UPW];
+    float pg[TPC][4][UPW];
+    bool row_ok[TPC];
+    const float* pre_row[TPC];
+    size_t out_row[TPC], hx_off[TPC];
+    unsigned int* counter[TPC];
 #pragma unroll
-    for (int j = 0; j < UPW; ++j) c_state[j] = 0.f;
-    const float* pre_row = p.pre + (size_t)(row_ok ? b : 0) * p.T * 4 * H + u_glb;
-    const size_t out_row = (size_t)(row_ok ? b : 0) * p.T * H + u_glb;
-    // exchange-buffer position of this thread's units: plane = u_glb / 8, element = u_glb % 8
-    const size_t hx_off = (size_t)m * hx_tile + ((size_t)(u_glb >> 3) * LM + row) * 8 + (u_glb & 7);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float pg[4][UPW];
-    // prefetch pre-activations of step 0
+    for (int j = 0; j < TPC; ++j) {
+      const int m = (int)blockIdx.y + j * (int)gridDim.y;
+      const int b = m * LM + row;
+      row_ok[j] = j < ntile && b < p.B;
+      pre_row[j] = p.pre + (size_t)(row_ok[j] ? b : 0) * p.T * 4 * H + u_glb;
+      out_row[j] = (size_t)(row_ok[j] ? b : 0) * p.T * H + u_glb;
+      // exchange-buffer position of this thread's units: plane = u_glb / 8, element = u_glb % 8
+      hx_off[j] = (size_t)(j < ntile ? m : 0) * hx_tile + ((size_t)(u_glb >> 3) * LM + row) * 8 + (u_glb & 7);
+      counter[j] = p.counters + (j < ntile ? m : 0) * CNT_STRIDE + (n * U) / KC;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+      for (int u = 0; u < UPW; ++u) c_state[j][u] = 0.f;
+      // prefetch pre-activations of step 0
 #pragma unroll
-      for (int j = 0; j < UPW; ++j) pg[g][j] = row_ok ? __ldcs(pre_row + (size_t)g * H + j) : 0.f;
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) pg[j][g][u] = row_ok[j] ? __ldcs(pre_row[j] + (size_t)g * H + u) : 0.f;
+    }
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < p.T; ++t) {
-      mbar_wait(bar_accf, (uint32_t)t & 1u);
-      tc_fence_after();
-      if (gw == 0 && lane == 0) LTRACE(3);
-      uint32_t acc[4][UPW];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if constexpr (UPW == 4) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(acc[g][0]), "=r"(acc[g][1]), "=r"(acc[g][2]), "=r"(acc[g][3])
-                       : "r"(taddr + (uint32_t)(g * U + u_loc)));
-        } else {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
-                       : "=r"(acc[g][0]), "=r"(acc[g][1])
-                       : "r"(taddr + (uint32_t)(g * U + u_loc)));
-        }
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acce);
-      float hv[UPW];
+      for (int j = 0; j < TPC; ++j) {
+        if (j >= ntile) break;
+        mbar_wait(bar_accf + 8u * j, (uint32_t)t & 1u);
+        tc_fence_after();
+        if (gw == 0 && lane == 0) LTRACE(3);
+        const uint32_t taddr = taddr0 + (uint32_t)j * acc_cols;
+        uint32_t acc[SPLIT][4][UPW];
 #pragma unroll
-      for (int j = 0; j < UPW; ++j) {
-        const float gi = __uint_as_float(acc[0][j]) + pg[0][j];
-        const float gf = __uint_as_float(acc[1][j]) + pg[1][j];
-        const float gg = __uint_as_float(acc[2][j]) + pg[2][j];
-        const float go = __uint_as_float(acc[3][j]) + pg[3][j];
-        const float c = fmaf(sigmoid_acc(gf), c_state[j], sigmoid_acc(gi) * tanh_acc(gg));
-        c_state[j] = c;
-        hv[j] = sigmoid_acc(go) * tanh_acc(c);
-      }
-      // publish h_t (bf16 hi[/lo]) for the next step's MMA, in the UMMA K-major image -- FIRST: every other CTA of
-      // this batch tile waits for it.  The fences below wait for all earlier memory operations of the thread, so
-      // nothing else (output store, skip load, next step's pre-activation loads) may be in flight before them.
-      {
-        __nv_bfloat16* dst = p.hx + (size_t)(t & 1) * hx_parity + hx_off;
-        __nv_bfloat16 hi[UPW], lo[UPW];
+        for (int sp = 0; sp < SPLIT; ++sp)
 #pragma unroll
-        for (int j = 0; j < UPW; ++j) {
-          hi[j] = __float2bfloat16_rn(hv[j]);
-          lo[j] = __float2bfloat16_rn(hv[j] - __bfloat162float(hi[j]));
-        }
-        if constexpr (UPW == 4) {
-          *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hi);
-          if (SPLIT == 2) *reinterpret_cast<uint2*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint2*>(lo);
-        } else {
-          *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(hi);
-          if (SPLIT == 2) *reinterpret_cast<uint32_t*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint32_t*>(lo);
-        }
-      }
-      // make the h stores visible: generic -> async proxy per thread, then the CTA barrier orders every gate
-      // thread's stores before ONE release-increment at gpu scope (release is cumulative over the barrier, the
-      // pattern of a grid barrier) -- a per-thread __threadfence before the barrier cost one more L2 round trip
-      // on the step's critical path (8.8 -> 8.0 us per step).  Polling the chunk counters from one lane per chunk
-      // instead of one after the other was measured slower (9.1 us: four times the polling traffic on four hot words).
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      if (gw == 0 && lane == 0) LTRACE(4);
-      asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
-      if (gw == 0 && lane == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + m * CNT_STRIDE + (n * U) / KC) : "memory");
-        LTRACE(5);
-      }
-      // off the critical path (overlaps the other CTAs' publishes, the h copies and the next MMA phase):
-      // next step's pre-activations and this step's output row
-      if (t + 1 < p.T) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int j = 0; j < UPW; ++j) pg[g][j] = row_ok ? __ldcs(pre_row + (size_t)(t + 1) * 4 * H + (size_t)g * H + j) : 0.f;
-      }
-      if (row_ok) {
-        const size_t o = out_row + (size_t)t * H;
-        if constexpr (UPW == 4) {
-          float4 v = make_float4(hv[0], hv[1], hv[2], hv[3]);
-          if (p.skip) {
-            const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.skip + o));
-            v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t col = taddr + (uint32_t)(sp * NS + g * U + u_loc);
+            if constexpr (UPW == 4) {
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(acc[sp][g][0]), "=r"(acc[sp][g][1]), "=r"(acc[sp][g][2]), "=r"(acc[sp][g][3])
+                           : "r"(col));
+            } else {
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                           : "=r"(acc[sp][g][0]), "=r"(acc[sp][g][1])
+                           : "r"(col));
+            }
           }
-          __stcs(reinterpret_cast<float4*>(p.y + o), v);
-        } else {
-          float2 v = make_float2(hv[0], hv[1]);
-          if (p.skip) {
-            const float2 s2 = __ldcs(reinterpret_cast<const float2*>(p.skip + o));
-            v.x += s2.x; v.y += s2.y;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acce + 8u * j);
+        float hv[UPW];
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) {
+          float a4[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float a = __uint_as_float(acc[0][g][u]);
+            if (SPLIT == 2) a += __uint_as_float(acc[SPLIT - 1][g][u]);    // (hi*hi + lo*hi) + hi*lo
+            a4[g] = a + pg[j][g][u];
           }
-          __stcs(reinterpret_cast<float2*>(p.y + o), v);
+          const float c = fmaf(sigmoid_acc(a4[1]), c_state[j][u], sigmoid_acc(a4[0]) * tanh_acc(a4[2]));
+          c_state[j][u] = c;
+          hv[u] = sigmoid_acc(a4[3]) * tanh_acc(c);
+        }
+        // publish h_t (bf16 hi[/lo]) for the next step's MMA, in the UMMA K-major image -- FIRST: every other CTA of
+        // this batch tile waits for it.  The fences below wait for all earlier memory operations of the thread, so
+        // nothing else (output store, skip load, next step's pre-activation loads) may be in flight before them.
+        {
+          __nv_bfloat16* dst = p.hx + (size_t)(t & 1) * hx_parity + hx_off[j];
+          __nv_bfloat16 hi[UPW], lo[UPW];
+#pragma unroll
+          for (int u = 0; u < UPW; ++u) {
+            hi[u] = __float2bfloat16_rn(hv[u]);
+            lo[u] = __float2bfloat16_rn(hv[u] - __bfloat162float(hi[u]));
+          }
+          if constexpr (UPW == 4) {
+            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hi);
+            if (SPLIT == 2) *reinterpret_cast<uint2*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint2*>(lo);
+          } else {
+            *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(hi);
+            if (SPLIT == 2) *reinterpret_cast<uint32_t*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint32_t*>(lo);
+          }
+        }
+        // make the h stores visible: generic -> async proxy per thread, then the CTA barrier orders every gate
+        // thread's stores before ONE release-increment at gpu scope (release is cumulative over the barrier, the
+        // pattern of a grid barrier) -- a per-thread __threadfence before the barrier cost one more L2 round trip
+        // on the step's critical path (8.8 -> 8.0 us per step).  Polling the chunk counters from one lane per chunk
+        // instead of one after the other was measured slower (9.1 us: four times the polling traffic on four hot words).
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (gw == 0 && lane == 0) LTRACE(4);
+        asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
+        if (gw == 0 && lane == 0) {
+          LTRACE(6);
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter[j]) : "memory");
+          LTRACE(5);
+        }
+        // off the critical path (overlaps the other CTAs' publishes, the h copies and the next MMA phase):
+        // next step's pre-activations and this step's output row
+        if (t + 1 < p.T) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int u = 0; u < UPW; ++u)
+              pg[j][g][u] = row_ok[j] ? __ldcs(pre_row[j] + (size_t)(t + 1) * 4 * H + (size_t)g * H + u) : 0.f;
+        }
+        if (row_ok[j]) {
+          const size_t o = out_row[j] + (size_t)t * H;
+          if constexpr (UPW == 4) {
+            float4 v = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            if (p.skip) {
+              const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.skip + o));
+              v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+            }
+            __stcs(reinterpret_cast<float4*>(p.y + o), v);
+          } else {
+            float2 v = make_float2(hv[0], hv[1]);
+            if (p.skip) {
+              const float2 s2 = __ldcs(reinterpret_cast<const float2*>(p.skip + o));
+              v.x += s2.x; v.y += s2.y;
+            }
+            __stcs(reinterpret_cast<float2*>(p.y + o), v);
+          }
         }
       }
     }
@@ -287,16 +338,25 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NS < 32 ? 32 : NS)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
 long long* g_lstm_trace = nullptr;
 
 struct LstmTcPlan {
-  int NS, nslot, n_slices, m_tiles, split;
+  int NS, nslot, n_slices, m_tiles, split, tpc, grid_y;
   size_t smem, hx_bytes, ws_bytes;
 };
+
+int device_sms() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  return sms;
+}
 
 bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   if (precision == BC_PREC_FP32) return false;
@@ -312,9 +372,14 @@ bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   while (nslot > 2 && w + nslot * slot + 1024 > 225 * 1024) --nslot;
   if (w + nslot * slot + 1024 > 225 * 1024) return false;
   pl->nslot = nslot;
-  pl->smem = w + nslot * slot + (2 * nslot + 3) * 8 + 64;
+  pl->smem = w + nslot * slot + (2 * nslot + 2 * MAX_TPC + 1) * 8 + 64;
   pl->hx_bytes = (size_t)2 * pl->m_tiles * pl->split * (H / 8) * LM * 8 * 2;
   pl->ws_bytes = pl->hx_bytes + (size_t)pl->m_tiles * CNT_STRIDE * sizeof(unsigned int) + 256;
+  // one batch tile per CTA while the tiles fit side by side (the latency-optimal shape); otherwise two independent
+  // tiles per CTA, interleaved step by step
+  const int side_by_side = device_sms() / pl->n_slices;
+  pl->tpc = (pl->m_tiles > side_by_side && bc::policy().lstm_pingpong) ? 2 : 1;
+  pl->grid_y = (pl->m_tiles + pl->tpc - 1) / pl->tpc;
   return true;
 }
 
@@ -333,13 +398,8 @@ extern "C" int bc_lstm_tc_slice_cols(int precision) {
 extern "C" int bc_lstm_tc_max_batch(int H, int precision) {
   LstmTcPlan pl;
   if (!lstm_tc_plan(128, H, precision, &pl)) return 0;
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-    cudaGetLastError();
-    sms = 148;
-  }
-  const int m_tiles = sms / pl.n_slices;
-  return m_tiles * LM;
+  const int m_tiles = device_sms() / pl.n_slices;
+  return m_tiles * LM * (bc::policy().lstm_pingpong ? MAX_TPC : 1);
 }
 
 extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, const float* skip, float* y,
@@ -357,22 +417,25 @@ extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) return bc::fail(BC_ENODEVICE, "lstm_tc: device does not support cooperative launch");
-  if (pl.n_slices * pl.m_tiles > sms)
-    return bc::fail(BC_EUNSUPPORTED, "lstm_tc: B=%d needs %d co-resident CTAs, device has %d SMs (split the batch)", B, pl.n_slices * pl.m_tiles, sms);
+  if (pl.n_slices * pl.grid_y > sms)
+    return bc::fail(BC_EUNSUPPORTED, "lstm_tc: B=%d needs %d co-resident CTAs, device has %d SMs (split the batch)", B, pl.n_slices * pl.grid_y, sms);
   LstmTcParams p;
   p.trace = g_lstm_trace;
   p.pre = pre; p.wimg = reinterpret_cast<const uint4*>(w_image); p.skip = skip; p.y = y;
   p.hx = reinterpret_cast<__nv_bfloat16*>(workspace);
   p.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + ((pl.hx_bytes + 127) & ~size_t(127)));
-  p.B = B; p.T = T; p.H = H; p.NS = pl.NS; p.nslot = pl.nslot; p.n_slices = pl.n_slices;
-  p.idesc = bc::tc::idesc_bf16_m128(pl.NS);
+  p.B = B; p.T = T; p.H = H; p.NS = pl.NS; p.nslot = pl.nslot; p.n_slices = pl.n_slices; p.m_tiles = pl.m_tiles;
+  p.idesc_wide = bc::tc::idesc_bf16_m128(pl.split * pl.NS);
+  p.idesc_ns = bc::tc::idesc_bf16_m128(pl.NS);
   cudaError_t e = cudaMemsetAsync(workspace, 0, pl.ws_bytes, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaMemsetAsync(lstm_tc)");
-  void* kern = pl.split == 2 ? (void*)lstm_tc_kernel<2, 2> : (void*)lstm_tc_kernel<1, 4>;
+  void* kern = nullptr;
+  if (pl.split == 2) kern = pl.tpc == 2 ? (void*)lstm_tc_kernel<2, 2, 2> : (void*)lstm_tc_kernel<2, 2, 1>;
+  else               kern = pl.tpc == 2 ? (void*)lstm_tc_kernel<1, 4, 2> : (void*)lstm_tc_kernel<1, 4, 1>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(lstm_tc)");
   void* args[] = {(void*)&p};
-  e = cudaLaunchCooperativeKernel(kern, dim3(pl.n_slices, pl.m_tiles), dim3(L_THREADS), args, pl.smem, st);
+  e = cudaLaunchCooperativeKernel(kern, dim3(pl.n_slices, pl.grid_y), dim3(L_THREADS), args, pl.smem, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaLaunchCooperativeKernel(lstm_tc)");
   return BC_OK;
 }

@@ -93,7 +93,7 @@ def prepare_waveform(waveform: torch.Tensor, sample_rate: int, target_sample_rat
 
 
 def extract_to_directory(model, items: Iterable[Tuple[torch.Tensor, str, str]], output_dir: str, *,
-                         micro_batch: int = 8, rnn_batch: int = 256, group_size: int = 256, writers: int = 4,
+                         micro_batch: int = 8, rnn_batch: int = 512, group_size: int = 256, writers: int = 4,
                          max_buffered_bytes: int = 2 << 30, max_buffered_items: int = 4096,
                          verbose: bool = True) -> Tuple[int, int]:
     """Encode ``items`` = (waveform float32 [T] or [1, T] at the codec rate, subset, fileid) and write one ``.npy``

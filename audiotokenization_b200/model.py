@@ -183,13 +183,13 @@ class BigCodecModel(nn.Module):
         return ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
 
     @torch.no_grad()
-    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256,
+    def indices_device(self, x_dev: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 512,
                        deep_batch: int = 64) -> torch.Tensor:
         """Device waveforms [N,1,T] -> int16 [N,T',n_q] on the device.
 
         Two-stage schedule: the convolutional front end runs in micro-batches (bounded activation
         memory: the stem's [mb, T, ngf] tensor is the largest), its frame-rate output (2 KB per frame) is
-        collected for up to ``rnn_batch`` utterances, and the sequential LSTM + final conv + VQ then run
+        collected for up to ``rnn_batch`` utterances (512: four 128-row tiles, two per CTA of the tensor-core LSTM kernel), and the sequential LSTM + final conv + VQ then run
         once over that whole group.  Inside the front end the last strided stages run over ``deep_batch``
         utterances at a time (`_FrontPipeline`)."""
         outs = []
@@ -233,7 +233,7 @@ class BigCodecModel(nn.Module):
             return self._indices_from_features(feat)
 
     @torch.no_grad()
-    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 256,
+    def extract_indices(self, wave_host: torch.Tensor, micro_batch: int = 8, rnn_batch: int = 512,
                         deep_batch: int = 64) -> np.ndarray:
         """Host (ideally pinned) float32 waveforms [N,1,T] -> int16 numpy [N,T',n_q].
 

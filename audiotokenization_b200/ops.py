@@ -338,7 +338,9 @@ def lstm_tc_max_batch(H: int, precision: str) -> int:
 
 
 def pack_lstm_tc_weight(w_hh: torch.Tensor, precision: str) -> torch.Tensor:
-    """W_hh [4H, H] fp32 -> bf16 image [4H/NS][split][H/16][2][NS][8] of bc_lstm_tc_recurrent_fwd."""
+    """W_hh [4H, H] fp32 -> bf16 image [4H/NS][H/16][2][split*NS][8] of bc_lstm_tc_recurrent_fwd: per 16-channel group
+    and k-plane the NS rows of the hi slice followed (split precision) by the NS rows of the lo slice, so that
+    [w_hi | w_lo] is one tcgen05 B operand of 2*NS rows."""
     NS = int(load_library().bc_lstm_tc_slice_cols(PRECISIONS[precision]))
     H = w_hh.shape[1]
     U = NS // 4
@@ -351,7 +353,7 @@ def pack_lstm_tc_weight(w_hh: torch.Tensor, precision: str) -> torch.Tensor:
     parts = [image(hi)]
     if precision == "bf16x3":
         parts.append(image((w - hi.float()).to(torch.bfloat16)))
-    return torch.stack(parts, dim=1).contiguous()
+    return torch.cat(parts, dim=3).contiguous()
 
 
 def lstm_recurrent_tc(pre: torch.Tensor, w_image: torch.Tensor, skip: Optional[torch.Tensor], precision: str,

@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("BC_MICRO_BATCH", "8")))
     ap.add_argument("--deep-batch", type=int, default=int(os.environ.get("BC_DEEP_BATCH", "64")),
                     help="clips per launch of the last strided stages of the conv stack (model._FrontPipeline)")
-    ap.add_argument("--rnn-batch", type=int, default=int(os.environ.get("BC_RNN_BATCH", "256")))
+    ap.add_argument("--rnn-batch", type=int, default=int(os.environ.get("BC_RNN_BATCH", "512")))
     ap.add_argument("--cpu-sample-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write a per-layer timing table (markdown) here")

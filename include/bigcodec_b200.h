@@ -174,8 +174,10 @@ int bc_lstm_recurrent_fwd(const float* pre, const float* w_hh_packed, const floa
 
 /* Tensor-core recurrence (BC_PREC_BF16 / BC_PREC_BF16X3): W_hh slices resident in shared memory, h
  * exchanged between CTAs as bf16 (hi[, lo]) UMMA images through HBM/L2, per-batch-tile step counters
- * instead of a grid barrier.  w_image = [4H/NS slices][split][H/16][2][NS][8] bf16 with slice row
- * g*(NS/4)+u = W_hh[g*H + slice*(NS/4) + u], NS = bc_lstm_tc_slice_cols(precision).
+ * instead of a grid barrier.  w_image = [4H/NS slices][H/16][2][split*NS][8] bf16: per 16-channel group and
+ * k-plane the NS rows of the hi slice, then (split = 2) the NS rows of the lo slice (one B operand of 2*NS rows);
+ * slice row g*(NS/4)+u = W_hh[g*H + slice*(NS/4) + u], NS = bc_lstm_tc_slice_cols(precision).
+ * Batches that do not fit one 128-row tile per CTA run two independent tiles per CTA, interleaved step by step.
  * bc_lstm_tc_max_batch: largest B one launch accepts on the current device (0 = no tensor-core plan for
  * this H; use bc_lstm_recurrent_fwd).  Workspace need not be zeroed.
  * Gate non-linearities in these modes use the SFU exponential and the approximate divide (|error| ~2e-7,

@@ -28,7 +28,7 @@ for prec in ("bf16", "bf16x3"):
 # per-phase timeline of CTA (0,0), steps 100..163 (B = 256, split precision)
 from audiotokenization_b200 import _cabi
 lib = _cabi.load_library()
-for prec, B in (("bf16x3", 256), ("bf16x3", 64), ("bf16", 256)):
+for prec, B in (("bf16x3", 512), ("bf16x3", 256), ("bf16", 512)):
     lstm = M.ResLSTM(H, num_layers=1).cuda()
     img = lstm.lstm.recurrent_image_for(0, prec)
     mb = ops.lstm_tc_max_batch(H, prec)
@@ -41,7 +41,7 @@ for prec, B in (("bf16x3", 256), ("bf16x3", 64), ("bf16", 256)):
     torch.cuda.synchronize()
     lib.bc_debug_set_lstm_trace(None)
     t = trace.cpu().view(64, 8).double()
-    names = ["counter seen", "h copies issued", "MMAs issued", "gates start (acc ready)", "h stored+fenced", "published"]
+    names = ["counter seen", "h copies issued", "MMAs issued", "gates start (acc ready)", "h stored+fenced", "published", "after bar.sync", "gates start (warp 15)"]
     step = (t[1:, 5] - t[:-1, 5]).mean()
     print(f"{prec} B={B}: {step:.0f} cycles per step; phase offsets from the previous step's publish:")
     for j, n in enumerate(names):

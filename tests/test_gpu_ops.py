@@ -405,7 +405,7 @@ def test_fused_residual_unit_matches_oracle(precision, tol, C, dil, causal, T):
 
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
 @pytest.mark.parametrize("H,layers,B,T", [(128, 2, 1, 1), (128, 1, 3, 40), (512, 2, 130, 25), (256, 2, 33, 64),
-                                          (512, 1, 257, 7)])
+                                          (512, 1, 257, 7), (512, 2, 512, 30), (512, 1, 300, 33), (256, 1, 385, 12)])
 def test_res_lstm_tensor_core_recurrence(precision, tol, H, layers, B, T):
     """tcgen05 recurrence (W_hh resident in smem, h exchanged as bf16 hi/lo images, per-tile step counters):
     several batch tiles, partial tiles, one-step sequences; and it must agree with the CUDA-core kernel."""
