@@ -419,9 +419,16 @@ int resunit_persist_fwd(const float* x, const float* w7, const float* b7, const 
                         const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
                         int C, int K, int dilation, int pad_left, int precision, cudaStream_t st);
 
+int ru_pair_layout(int C, int K, int dilation, int precision);
+int resunit_pair_fwd(const float* x, const void* w7_pair, const float* b7, const float* sa1, const float* sib1,
+                     const void* w1_pair, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T,
+                     int C, int K, int dilation, int pad_left, int precision, cudaStream_t st);
+
 int resunit_tc_fwd(const float* x, const float* w7, const float* b7, const float* sa1, const float* sib1,
                    const float* w1, const float* b1, const float* sa2, const float* sib2, float* y, int B, int T, int C,
                    int K, int dilation, int pad_left, int precision, cudaStream_t st) {
+  if (ru_pair_layout(C, K, dilation, precision) > 0)      // CTA-pair kernel: w7 / w1 are the per-rank pair images
+    return resunit_pair_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, st);
   if (ru_persist_slots(C, K, dilation, precision) > 0 && ru_group_groups(C, K, dilation, precision) > 0)
     return resunit_group_fwd(x, w7, b7, sa1, sib1, w1, b1, sa2, sib2, y, B, T, C, K, dilation, pad_left, precision, st);
   if (ru_persist_slots(C, K, dilation, precision) > 0)
@@ -465,6 +472,11 @@ extern "C" int bc_resunit_plan(int C, int K, int dilation, int precision, int* n
                                int* persistent) {
   if (!n_tile || !gpc || !nchunks || !persistent) return bc::fail(BC_EINVAL, "resunit_plan: null output");
   if (precision == BC_PREC_FP32) return bc::fail(BC_EUNSUPPORTED, "resunit_plan: tensor-core modes only");
+  if (bc::ru_pair_layout(C, K, dilation, precision) > 0) {
+    *n_tile = C; *gpc = C / 16; *nchunks = 1;
+    *persistent = 2 + bc::ru_pair_layout(C, K, dilation, precision);           // 3: CTA-pair kernel, plain image; 4: stacked image
+    return BC_OK;
+  }
   if (bc::ru_persist_slots(C, K, dilation, precision) > 0) {
     *n_tile = C; *gpc = C / 16; *nchunks = 1;
     *persistent = bc::ru_group_groups(C, K, dilation, precision) > 0 ? 2 : 1;   // 2: warpgroup-per-tile kernel, 1: role pipeline

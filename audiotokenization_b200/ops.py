@@ -142,7 +142,8 @@ def resunit(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, 
     flops = 2.0 * B * T * C * C * (k + 1)
     plan = resunit_plan(C, k, dilation, precision)
     with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device,
-                {1: "ru_persist_kernel", 2: "ru_group_kernel"}.get(plan[1] if plan else 0, "conv1d_tc_kernel"), 8.0 * B * T * C):
+                {1: "ru_persist_kernel", 2: "ru_group_kernel", 3: "ru_pair_kernel", 4: "ru_pair_kernel"}.get(plan[1] if plan else 0, "conv1d_tc_kernel"),
+                8.0 * B * T * C):
         check(load_library().bc_resunit_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1), ptr(sa2),
                                             ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left, PRECISIONS[precision],
                                             stream_ptr(x.device)), "bc_resunit_fwd")
@@ -227,6 +228,28 @@ def pack_tc_weight(w_kio: torch.Tensor, plan, precision: str) -> torch.Tensor:
     if precision == "bf16x3":
         parts.append(image((w - hi.float()).to(torch.bfloat16)))
     return torch.stack(parts, dim=2).contiguous()
+
+
+def pack_pair_weights(w_kio: torch.Tensor, stacked: bool) -> torch.Tensor:
+    """fp32 [K, C_in, C_out] -> the per-rank bf16 images of the CTA-pair ResidualUnit kernel (bc_resunit_plan kinds 3 / 4):
+    [2 ranks][...], see include/bigcodec_b200.h."""
+    K, c_in, c_out = w_kio.shape
+    w = w_kio.float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    half = c_out // 2
+
+    def block(m, r0, r1):   # rows [r0, r1) of m -> [K][c_in/16][2][rows][8], flattened
+        t = m[:, :, r0:r1]
+        return t.reshape(K, c_in // 16, 2, 8, r1 - r0).permute(0, 1, 2, 4, 3).reshape(-1)
+
+    ranks = []
+    for r in range(2):
+        if stacked:
+            ranks.append(torch.cat([block(hi if r == 0 else lo, 0, c_out), block(hi, r * half, (r + 1) * half)]))
+        else:
+            ranks.append(torch.cat([block(hi, r * half, (r + 1) * half), block(lo, r * half, (r + 1) * half)]))
+    return torch.stack(ranks).contiguous()
 
 
 def stream_plan(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision: str, fused: bool = False):

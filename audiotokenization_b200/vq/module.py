@@ -329,7 +329,7 @@ class ResidualUnit(nn.Module):
         plan = ops.resunit_plan(C, conv7.kernel_size, conv7.dilation, precision)
         if plan is None:
             return None
-        return conv7, conv1, plan[0], (C, C // 16, 1)
+        return conv7, conv1, plan[0], (C, C // 16, 1), plan[1]
 
     def _stream_forward(self, x_cl, prec, out=None):
         """Whole unit on the streamed-weight kernel (wide layers), or None."""
@@ -364,13 +364,17 @@ class ResidualUnit(nn.Module):
         if fused is None:
             h = _act_conv(self.block[0], self.block[1], x_cl)
             return _act_conv(self.block[2], self.block[3], h, res=x_cl)
-        conv7, conv1, plan7, plan1 = fused
+        conv7, conv1, plan7, plan1, kind = fused
         cache = self.__dict__.setdefault("_ru_cache", {})
-        key = (prec, plan7, conv7._key(), conv1._key())
+        key = (prec, plan7, kind, conv7._key(), conv1._key())
         if cache.get("key") != key:
             cache.clear()
-            cache.update(key=key, w7=ops.pack_tc_weight(conv7.packed()[0], plan7, prec),
-                         w1=ops.pack_tc_weight(conv1.packed()[0], plan1, prec))
+            if kind in (3, 4):    # CTA-pair kernel: per-rank images (half of every B operand per SM)
+                cache.update(key=key, w7=ops.pack_pair_weights(conv7.packed()[0], stacked=(kind == 4)),
+                             w1=ops.pack_pair_weights(conv1.packed()[0], stacked=False))
+            else:
+                cache.update(key=key, w7=ops.pack_tc_weight(conv7.packed()[0], plan7, prec),
+                             w1=ops.pack_tc_weight(conv1.packed()[0], plan1, prec))
         sa1, sib1 = self.block[0].act.device_params()
         sa2, sib2 = self.block[2].act.device_params()
         return ops.resunit(x_cl, cache["w7"], conv7.packed()[1], sa1, sib1, cache["w1"], conv1.packed()[1], sa2, sib2,

@@ -326,7 +326,7 @@ def main():
     step_ms = ms_total / args.steps
     peaks = load_peaks()
     # dominant kernel = the tcgen05 convolution kernel family with the largest share of the step
-    conv_kernels = {k: v for k, v in by_kernel.items() if k in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel")}
+    conv_kernels = {k: v for k, v in by_kernel.items() if k in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel")}
     dom = max(conv_kernels, key=lambda k: conv_kernels[k][1]) if conv_kernels else None
     d_fl, d_ms, d_n, d_bytes, d_ms_hbm = conv_kernels[dom] if dom else (0.0, 0.0, 0, 0.0, 0.0)
     # which roof bounds it: arithmetic intensity of its launches against the ridge of the measured peaks

@@ -119,7 +119,14 @@ int bc_tc_plan(int C_in, int C_out, int K, int stride, int dilation, int precisi
 /* Weight-image geometry bc_resunit_fwd expects for W7 (same meaning as bc_tc_plan; W1 is always
  * n_tile = C, gpc = C/16, nchunks = 1).  *persistent = 1 when the persistent warp-specialised kernel
  * (weights resident in shared memory, C in {16,32,64}) will run, 2 when its warpgroup-per-tile form does
- * (same weight images; csrc/ru_group.cu), 0 for the per-tile kernel. */
+ * (same weight images; csrc/ru_group.cu), 0 for the per-tile kernel.
+ * *persistent = 3 / 4: the CTA-pair kernel (tcgen05 cta_group::2, csrc/ru_pair.cu; C = 64, split precision) runs and
+ * w7 / w1 must be its PER-RANK images, two consecutive blocks (rank 0, rank 1) of equal size.  A block of rows R of a
+ * bf16 matrix m[k][c_in][n] is laid out [k][c_in/16][2 k-planes][|R|][8]  (channel = g*16 + h*8 + e).  With hi = bf16(w),
+ * lo = bf16(w - hi) and half(r) = rows [r*C/2, (r+1)*C/2):
+ *   3 (plain)    w7 rank r = block(hi, half(r)) | block(lo, half(r))
+ *   4 (stacked)  w7 rank r = block(r == 0 ? hi : lo, all rows) | block(hi, half(r))
+ *   w1 (both)    rank r = block(hi, half(r)) | block(lo, half(r)) */
 int bc_resunit_plan(int C, int K, int dilation, int precision, int* n_tile, int* gpc, int* nchunks, int* persistent);
 int bc_resunit_fwd(const float* x, const float* w7, const float* b7, const float* snake1_a, const float* snake1_ib,
                    const float* w1, const float* b1, const float* snake2_a, const float* snake2_ib, float* y,

@@ -27,7 +27,7 @@ def timeit(fn, n=5):
 
 
 rows = []
-cases = [("ru", 128, 9, 60000), ("ru", 256, 9, 12000), ("ru", 128, 1, 60000), ("ru", 64, 9, 240000), ("ru", 32, 9, 480000),
+cases = [("ru", 64, 1, 240000), ("ru", 64, 3, 240000), ("ru", 128, 9, 60000), ("ru", 256, 9, 12000), ("ru", 128, 1, 60000), ("ru", 64, 9, 240000), ("ru", 32, 9, 480000),
          ("conv", 32, 64, 4, 2, 480000), ("conv", 64, 128, 8, 4, 240000), ("conv", 128, 256, 10, 5, 60000),
          ("conv", 256, 512, 10, 5, 12000), ("conv", 512, 2048, 1, 1, 2400 * 8), ("conv", 512, 512, 3, 1, 2400 * 8)]
 for c in cases:

@@ -88,7 +88,7 @@ def traffic(path, out_json, precision):
     agg = {}
     for r in rd:
         name = r["Kernel Name"]
-        fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel", "lstm_tc_kernel",
+        fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel", "lstm_tc_kernel",
                                 "stem_conv_kernel", "vq_encode_kernel") if f in name), None)
         if fam is None:
             continue

@@ -83,7 +83,7 @@ def test_tensor_core_split_mode_meets_the_fp32_contract(case):
         ops.PROFILE = prof
     assert ops.STATS["launches"] > n0
     if cfg["codec_encoder"]["ngf"] >= 16 and not g["antialias"]:
-        assert kernels & {"conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "conv1d_tc_kernel"}, kernels
+        assert kernels & {"conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel"}, kernels
     e_z = rel(z.cpu().numpy(), g["z_f64"])
     assert e_z <= 2e-4, e_z
     idx = out["indices"].cpu().numpy()

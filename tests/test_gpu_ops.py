@@ -403,6 +403,53 @@ def test_fused_residual_unit_matches_oracle(precision, tol, C, dil, causal, T):
     assert rel(got, unfused) <= tol
 
 
+_PAIR_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {repo!r}); sys.path.insert(0, {repo!r} + "/tests")
+from audiotokenization_b200.vq import module as M
+from oracle import bigcodec_oracle as oracle
+C = 64
+for dil, B, T in [(1, 3, 40000), (3, 1, 128 * 151), (9, 5, 9000), (9, 1, 100), (3, 2, 20000)]:
+    g = torch.Generator().manual_seed(1000 + dil + B + T)
+    ru = M.ResidualUnit(C, dilation=dil)
+    for name, prm in ru.named_parameters():
+        if name.endswith(("alpha", "beta")):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.3
+        elif name.endswith("bias"):
+            prm.data = torch.randn(prm.shape, generator=g) * 0.2
+    sd = {{name: prm.data.clone().double() for name, prm in ru.named_parameters()}}
+    x = torch.randn(B, C, T, generator=g)
+    want = oracle.residual_unit(sd, "", x.double(), dil, False, False)
+    ru = ru.cuda()
+    M.set_precision("bf16x3")
+    plan = ru._fused_plan("bf16x3")
+    assert plan is not None and plan[4] in (3, 4), plan          # the CTA-pair kernel is what runs
+    got = ru(x.cuda()); again = ru(x.cuda())
+    M.FUSE_RESUNIT[0] = False
+    unfused = ru(x.cuda())
+    M.FUSE_RESUNIT[0] = True
+    rel = lambda a, b: float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm())
+    assert torch.equal(got, again)
+    assert rel(got, want) <= 5e-5 and rel(got, unfused) <= 5e-5, (rel(got, want), rel(got, unfused))
+    err = (got.cpu().double() - want).abs().amax(dim=1)           # per time step: no tile may be wrong
+    assert float(err.max()) <= 2e-4 * max(1.0, float(want.abs().max())), (dil, B, T, int(err.argmax()))
+    print("pair ok", dil, B, T, plan[4])
+"""
+
+
+def test_cta_pair_residual_unit_many_tiles_odd_counts():
+    """ru_pair.cu (tcgen05 cta_group::2, C = 64, split precision; opt-in with BC_RU_PAIR=1, hence the subprocess): more
+    tile pairs than CTA pairs (every pair walks several rounds through both activation slots and accumulator stages),
+    odd tile counts (the phantom tile of rank 1), a single tile, tiles that straddle items, stacked and plain weight
+    images -- against the float64 oracle and the unfused two-launch path."""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BC_RU_PAIR="1")
+    r = subprocess.run([sys.executable, "-c", _PAIR_SCRIPT.format(repo=repo)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("pair ok") == 5, r.stdout
+
+
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
 @pytest.mark.parametrize("H,layers,B,T", [(128, 2, 1, 1), (128, 1, 3, 40), (512, 2, 130, 25), (256, 2, 33, 64),
                                           (512, 1, 257, 7), (512, 2, 512, 30), (512, 1, 300, 33), (256, 1, 385, 12)])
