@@ -1,19 +1,29 @@
 // Factorized VQ: in_proj -> L2 normalise -> cosine argmax over the codebook -> int32,
 // and the inverse (codebook gather + out_proj).  CUDA cores: the contraction depth is
-// the codebook dimension D = 8.
+// the codebook dimension D = 8, so the search is bound by the fp32 FMA pipe
+// (2*K*D FLOP against 2052 B per frame), not by HBM.
 //
-// Encode, per CTA of 8 warps = 32 frames:
-//   phase 1  warp w projects frames 4w..4w+3: lanes stride the C input channels
-//            (coalesced), D partial sums per frame, butterfly-reduced; then the
-//            projected vector is normalised exactly like F.normalize (x / max(|x|, 1e-12)).
-//   phase 2  the same warp scans the whole (pre-normalised) codebook for its 4 frames:
-//            lane l visits codes l, l+32, ... (coalesced 32-byte rows, L1/L2 resident),
-//            keeps top-1 / top-2 in registers; warp-shuffle merge, ties -> lowest index
-//            (torch.max semantics, factorized_vector_quantize.py:106).
+// Encode, per CTA of 256 threads = FR * 256 frames (D = 8: vq_scan_kernel; other D: the generic kernel below):
+//   phase 1  warp w projects its share of the CTA's frames, 4 at a time: lanes stride the C input channels
+//            (coalesced), D partial sums per frame, butterfly-reduced; the projected vector is normalised exactly
+//            like F.normalize (x / max(|x|, 1e-12)) and parked in shared memory.
+//   phase 2  every thread takes FR = 8 frames into registers (as 4 packed fp32 pairs) and scans the whole codebook,
+//            which streams through shared memory in tiles of 512 codes with every component DUPLICATED (c, c): one
+//            broadcast LDS.128 feeds two packed FMAs (fma.rn.f32x2: two frames per instruction, one issue slot),
+//            so a code costs 4 LDS + 32 FFMA2 + the top-1 bookkeeping (3 instructions per frame) for 64 FMAs -- the
+//            FMA pipe, not instruction issue, is the limit.  Codes are visited in increasing order by every thread
+//            and a strict > keeps the lowest index among equal values (torch.max semantics,
+//            factorized_vector_quantize.py:106): no cross-lane merge at all.  The top-2 bookkeeping (margin) is a
+//            template variant and only runs when a margin is requested.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <float.h>
 
 namespace {
+using bc::tc::f32x2;
+using bc::tc::fma2;
+using bc::tc::pack2;
+using bc::tc::unpack2;
 
 constexpr int VQ_WARPS = 8;
 constexpr int FPW = 4;  // frames per warp
@@ -43,6 +53,171 @@ __device__ __forceinline__ void top2_merge(Top2& a, float v1, float v2, int i1) 
     a.i1 = i1;
   } else {
     a.v2 = fmaxf(a.v2, v1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D = 8: register-tiled scan over a shared-memory-resident codebook tile
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_FR = 8;                         // frames per thread
+constexpr int SC_FRAMES = SC_THREADS * SC_FR;    // frames per CTA
+constexpr int SC_TK = 512;                       // codes per shared-memory tile
+constexpr int SC_D = 8;
+constexpr size_t SC_SMEM = (size_t)SC_FRAMES * SC_D * sizeof(float);   // 64 KB: projected frames, then two duplicated code tiles
+
+template <bool MARGIN>
+__global__ void __launch_bounds__(SC_THREADS, 2) vq_scan_kernel(const float* __restrict__ z, const float* __restrict__ w_in,
+                                                                const float* __restrict__ b_in, const float* __restrict__ cbn,
+                                                                int32_t* __restrict__ idx, float* __restrict__ margin,
+                                                                float* __restrict__ z_e_out, int N, int C, int Kc) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int D = SC_D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_base = (long long)blockIdx.x * SC_FRAMES;
+  const int n_here = (int)min((long long)SC_FRAMES, (long long)N - n_base);
+  float* sE = smem;                              // [SC_FRAMES][D] normalised projections (phase 1 -> phase 2 hand-off)
+
+  // ---- phase 1: projection + normalisation (w_in read through L1: 16 KB shared by all warps of the SM) ----
+  const bool proj = w_in != nullptr;
+  for (int f0 = warp * FPW; f0 < n_here; f0 += VQ_WARPS * FPW) {
+    float e[FPW][D];
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+#pragma unroll
+      for (int d = 0; d < D; ++d) e[f][d] = 0.f;
+    if (proj) {
+      for (int c = lane; c < C; c += 32) {
+        float zv[FPW];
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) zv[f] = (f0 + f < n_here) ? __ldcs(z + (size_t)(n_base + f0 + f) * C + c) : 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float w = __ldg(w_in + d * C + c);
+#pragma unroll
+          for (int f = 0; f < FPW; ++f) e[f][d] = fmaf(zv[f], w, e[f][d]);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < FPW; ++f)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          float v = e[f][d];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          e[f][d] = v + __ldg(b_in + d);
+        }
+    } else {
+#pragma unroll
+      for (int f = 0; f < FPW; ++f)
+#pragma unroll
+        for (int d = 0; d < D; ++d) e[f][d] = (f0 + f < n_here) ? __ldg(z + (size_t)(n_base + f0 + f) * C + d) : 0.f;
+    }
+    if (lane < FPW && f0 + lane < n_here) {       // lane f finishes frame f0 + f (every lane holds all sums after the butterfly)
+      float v[D];
+#pragma unroll
+      for (int f = 0; f < FPW; ++f)
+        if (lane == f) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) v[d] = e[f][d];
+        }
+      if (z_e_out) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) z_e_out[(size_t)(n_base + f0 + lane) * D + d] = v[d];
+      }
+      float ss = 0.f;                             // F.normalize: x / max(||x||_2, eps)
+#pragma unroll
+      for (int d = 0; d < D; ++d) ss = fmaf(v[d], v[d], ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      float4* dst = reinterpret_cast<float4*>(sE + (size_t)(f0 + lane) * D);
+      dst[0] = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+      dst[1] = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: this thread's frames tid, tid + 256, ... as packed pairs (frame 2p, frame 2p+1) ----
+  f32x2 e2[SC_FR / 2][D];
+#pragma unroll
+  for (int pp = 0; pp < SC_FR / 2; ++pp) {
+    const int fa = tid + SC_THREADS * (2 * pp), fb = fa + SC_THREADS;
+    float a[D], b[D];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 va = fa < n_here ? reinterpret_cast<const float4*>(sE + (size_t)fa * D)[h] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 vb = fb < n_here ? reinterpret_cast<const float4*>(sE + (size_t)fb * D)[h] : make_float4(0.f, 0.f, 0.f, 0.f);
+      a[4 * h] = va.x; a[4 * h + 1] = va.y; a[4 * h + 2] = va.z; a[4 * h + 3] = va.w;
+      b[4 * h] = vb.x; b[4 * h + 1] = vb.y; b[4 * h + 2] = vb.z; b[4 * h + 3] = vb.w;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) e2[pp][d] = pack2(a[d], b[d]);
+  }
+  __syncthreads();                                // sE is dead: the buffer becomes the two code tiles
+
+  float best[SC_FR], second[SC_FR];
+  int besti[SC_FR];
+#pragma unroll
+  for (int f = 0; f < SC_FR; ++f) { best[f] = -FLT_MAX; second[f] = -FLT_MAX; besti[f] = 0x7fffffff; }
+
+  // code tiles: [SC_TK][D][2] floats (component duplicated), double-buffered; filled by all threads with coalesced loads
+  float* sC0 = smem;
+  float* sC1 = smem + (size_t)SC_TK * D * 2;
+  auto fill = [&](float* dstT, int k0) {
+    // 2 codes per thread: one float4 pair (32 B) per code from global, 64 B duplicated into shared memory
+    for (int i = tid; i < SC_TK; i += SC_THREADS) {
+      const int k = k0 + i;
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+      if (k < Kc) {
+        lo = __ldg(reinterpret_cast<const float4*>(cbn + (size_t)k * D));
+        hi = __ldg(reinterpret_cast<const float4*>(cbn + (size_t)k * D) + 1);
+      }
+      float4* d4 = reinterpret_cast<float4*>(dstT + (size_t)i * D * 2);
+      d4[0] = make_float4(lo.x, lo.x, lo.y, lo.y);
+      d4[1] = make_float4(lo.z, lo.z, lo.w, lo.w);
+      d4[2] = make_float4(hi.x, hi.x, hi.y, hi.y);
+      d4[3] = make_float4(hi.z, hi.z, hi.w, hi.w);
+    }
+  };
+  fill(sC0, 0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < Kc; k0 += SC_TK, buf ^= 1) {
+    const float* cur = buf ? sC1 : sC0;
+    if (k0 + SC_TK < Kc) fill(buf ? sC0 : sC1, k0 + SC_TK);      // next tile: its global loads overlap this tile's scan
+    const int kend = min(SC_TK, Kc - k0);
+#pragma unroll 2
+    for (int i = 0; i < kend; ++i) {
+      const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(cur + (size_t)i * D * 2);   // broadcast: every lane reads the same code
+      const ulonglong2 c01 = cp[0], c23 = cp[1], c45 = cp[2], c67 = cp[3];
+      const f32x2 cd[D] = {c01.x, c01.y, c23.x, c23.y, c45.x, c45.y, c67.x, c67.y};
+      const int k = k0 + i;
+#pragma unroll
+      for (int pp = 0; pp < SC_FR / 2; ++pp) {
+        f32x2 acc = fma2(e2[pp][0], cd[0], pack2(0.f, 0.f));
+#pragma unroll
+        for (int d = 1; d < D; ++d) acc = fma2(e2[pp][d], cd[d], acc);
+        float da, db;
+        unpack2(acc, da, db);
+        if (MARGIN) {
+          if (da > best[2 * pp]) { second[2 * pp] = best[2 * pp]; best[2 * pp] = da; besti[2 * pp] = k; }
+          else if (da > second[2 * pp]) second[2 * pp] = da;
+          if (db > best[2 * pp + 1]) { second[2 * pp + 1] = best[2 * pp + 1]; best[2 * pp + 1] = db; besti[2 * pp + 1] = k; }
+          else if (db > second[2 * pp + 1]) second[2 * pp + 1] = db;
+        } else {
+          if (da > best[2 * pp]) { best[2 * pp] = da; besti[2 * pp] = k; }
+          if (db > best[2 * pp + 1]) { best[2 * pp + 1] = db; besti[2 * pp + 1] = k; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int f = 0; f < SC_FR; ++f) {
+    const int fr = tid + SC_THREADS * f;
+    if (fr < n_here) {
+      idx[n_base + fr] = besti[f];
+      if (MARGIN) margin[n_base + fr] = best[f] - second[f];
+    }
   }
 }
 
@@ -221,11 +396,28 @@ extern "C" int bc_vq_encode(const float* z, const float* w_in, const float* b_in
   BC_REQUIRE((w_in == nullptr) == (b_in == nullptr), "vq_encode: w_in and b_in must both be given or both NULL");
   if (!w_in) BC_REQUIRE(C == D, "vq_encode: identity projection needs C == D (C=%d D=%d)", C, D);
   BC_REQUIRE(bc::aligned16(cb_norm), "vq_encode: codebook must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)s;
+  if (D == SC_D && N >= SC_FRAMES / 2 && bc::aligned16(z)) {
+    // register-tiled scan over shared-memory code tiles (small calls keep the per-warp kernel: more CTAs than SMs there)
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(vq_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(vq_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(vq_scan)");
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const unsigned grid = (unsigned)(((long long)N + SC_FRAMES - 1) / SC_FRAMES);
+    if (margin) vq_scan_kernel<true><<<grid, SC_THREADS, SC_SMEM, st>>>(z, w_in, b_in, cb_norm, idx, margin, z_e, N, C, Kc);
+    else        vq_scan_kernel<false><<<grid, SC_THREADS, SC_SMEM, st>>>(z, w_in, b_in, cb_norm, idx, margin, z_e, N, C, Kc);
+    BC_LAUNCH_CHECK("vq_scan_kernel");
+    return BC_OK;
+  }
   const size_t smem = w_in ? (size_t)D * C * sizeof(float) : 0;
   if (smem > 200 * 1024) return bc::fail(BC_EUNSUPPORTED, "vq_encode: in_proj %dx%d does not fit shared memory", D, C);
   const int frames_per_cta = VQ_WARPS * FPW;
   const unsigned grid = (unsigned)((N + frames_per_cta - 1) / frames_per_cta);
-  cudaStream_t st = (cudaStream_t)s;
   VQ_DISPATCH_D(D, {
     if (smem > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(vq_encode_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

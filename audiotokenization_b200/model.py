@@ -178,7 +178,7 @@ class BigCodecModel(nn.Module):
     def _indices_from_features(self, feat):
         """frame-rate features [B,T',enc_dim] -> int16 [B,T',n_q] on the device."""
         z_cl = self.encoder.back_cl(feat)
-        _, idx, _ = self.decoder.quantizer.forward_cl(z_cl)
+        _, idx, _ = self.decoder.quantizer.forward_cl(z_cl, want_zq=False)    # index-only: no z_q is written
         n_q, B, Tp = idx.shape
         return ops.indices_to_int16(idx.reshape(n_q, B * Tp)).view(B, Tp, n_q)
 

@@ -17,18 +17,23 @@ class ResidualVQ(nn.Module):
         self.layers = nn.ModuleList([VQ(codebook_size=size, **kwargs) for size in codebook_size])
         self.num_quantizers = num_quantizers
 
-    def forward_cl(self, z_cl, want_margin=False):
-        """z_cl [B,T,C] -> (z_q [B,T,C], idx int32 [n_q,B,T], margins | None)."""
+    def forward_cl(self, z_cl, want_margin=False, want_zq=True):
+        """z_cl [B,T,C] -> (z_q [B,T,C] | None, idx int32 [n_q,B,T], margins | None).  ``want_zq=False`` (the
+        encode -> indices path of extract_indices.py, which drops the quantised latents) skips every dequantisation
+        the residual loop does not need: all of them for one quantizer, the last one otherwise."""
         B, T, C = z_cl.shape
         residual = z_cl.clone() if len(self.layers) > 1 else None
         z_q = None
         all_idx, margins = [], []
         for i, layer in enumerate(self.layers):
             idx, margin, _ = layer.encode_cl(z_cl if residual is None else residual, want_margin=want_margin)
-            # quantized_out += q ; residual -= q   (residual_vq.py:27-33) in one kernel
-            z_q = layer.dequant_cl(idx, z_q=z_q, residual=residual)
             all_idx.append(idx)
             margins.append(margin)
+            if not want_zq and i == len(self.layers) - 1:
+                z_q = None
+                break
+            # quantized_out += q ; residual -= q   (residual_vq.py:27-33) in one kernel
+            z_q = layer.dequant_cl(idx, z_q=z_q, residual=residual)
         return z_q, torch.stack(all_idx), (torch.stack(margins) if want_margin else None)
 
     @torch.no_grad()

@@ -43,7 +43,8 @@ def test_transpose_round_trip(B, C, T):
 
 @pytest.mark.parametrize("aa", [False, True])
 @pytest.mark.parametrize("B,C,T", [(1, 8, 1), (2, 32, 5), (1, 33, 31), (2, 64, 33), (1, 32, 1000), (3, 128, 257),
-                                   (1, 4, 4099)])
+                                   (1, 4, 4099), (1, 16, 126), (2, 32, 127), (2, 64, 756), (1, 256, 13), (1, 32, 6),
+                                   (1, 512, 2), (2, 16, 2521)])
 def test_activation1d_matches_oracle(aa, B, C, T):
     g = gen(B * 1000 + C + T)
     act = Activation1d(SnakeBeta(C, alpha_logscale=True), antialias=aa)
