@@ -48,6 +48,7 @@ _SIGNATURES = {
     "bc_lstm_tc_recurrent_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "bc_vq_encode": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "bc_fsq_encode": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
     "bc_code_histogram": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
     "bc_code_entropy": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "bc_debug_set_ru_trace": (c_int, [c_void_p]),

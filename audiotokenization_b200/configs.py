@@ -76,6 +76,10 @@ MODEL_CONFIGS["tiny"] = {
                           rnn_num_layers=2, up_ratios=[5, 4, 2], codebook_size=512),
 }
 
+# the tiny model with the decoder's other quantizer (fsq=True: vq/codec_decoder.py:41-47); 4*4*4*8 = 512 codes
+MODEL_CONFIGS["tiny_fsq"] = copy.deepcopy(MODEL_CONFIGS["tiny"])
+MODEL_CONFIGS["tiny_fsq"]["codec_decoder"].update(fsq=True, fsq_levels=[4, 4, 4, 8], codebook_size=512)
+
 SAMPLE_RATE = 16000  # config/dataset/default.yaml (dataset.sample_rate)
 
 

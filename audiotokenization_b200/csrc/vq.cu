@@ -330,6 +330,83 @@ __global__ void __launch_bounds__(VQ_WARPS * 32) vq_encode_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Finite scalar quantisation (the other quantizer BigCodecDecoder can select: vq/codec_decoder.py:41-47,87-89;
+// FSQ.forward / bound / quantize / codes_to_indices, finite_scalar_quantization.py:111-148,170-175,203-259):
+//   z_e = W_in z + b_in                      (nn.Linear dim -> d)
+//   bounded_j = tanh(z_e_j + shift_j) * half_l_j - offset_j
+//   q_j = round_half_even(bounded_j),  code_j = q_j / half_width_j
+//   index = int32( sum_j (code_j * half_width_j + half_width_j) * basis_j )
+// One warp per 4 frames: lanes stride the C input channels (coalesced), d partial sums per frame, butterfly-reduced;
+// HBM-bound (2 KB read per frame).  `boundary` (optional) receives min_j | bounded_j - nearest rounding boundary |.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(VQ_WARPS * 32) fsq_encode_kernel(const float* __restrict__ z, const float* __restrict__ w_in,
+                                                                   const float* __restrict__ b_in, const float* __restrict__ prm,
+                                                                   int32_t* __restrict__ idx, float* __restrict__ codes,
+                                                                   float* __restrict__ boundary, int N, int C) {
+  // prm: [5][D] = half_l | offset | shift | half_width | basis
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * VQ_WARPS + warp) * FPW;
+  if (n0 >= N) return;
+  float e[FPW][D];
+#pragma unroll
+  for (int f = 0; f < FPW; ++f)
+#pragma unroll
+    for (int d = 0; d < D; ++d) e[f][d] = 0.f;
+  if (w_in) {
+    for (int c = lane; c < C; c += 32) {
+      float zv[FPW];
+#pragma unroll
+      for (int f = 0; f < FPW; ++f) zv[f] = (n0 + f < N) ? __ldcs(z + (size_t)(n0 + f) * C + c) : 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float w = __ldg(w_in + d * C + c);
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) e[f][d] = fmaf(zv[f], w, e[f][d]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float v = e[f][d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        e[f][d] = v + (b_in ? __ldg(b_in + d) : 0.f);
+      }
+  } else {
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+#pragma unroll
+      for (int d = 0; d < D; ++d) e[f][d] = (n0 + f < N) ? __ldg(z + (size_t)(n0 + f) * C + d) : 0.f;
+  }
+  if (lane < FPW && n0 + lane < N) {
+    float v[D];
+#pragma unroll
+    for (int f = 0; f < FPW; ++f)
+      if (lane == f) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = e[f][d];
+      }
+    float sum = 0.f, bmin = FLT_MAX;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float half_l = __ldg(prm + d), offset = __ldg(prm + D + d), shift = __ldg(prm + 2 * D + d);
+      const float hw = __ldg(prm + 3 * D + d), basis = __ldg(prm + 4 * D + d);
+      const float bounded = __fsub_rn(__fmul_rn(tanhf(__fadd_rn(v[d], shift)), half_l), offset);
+      const float q = rintf(bounded);                                  // torch.round: half to even
+      const float code = __fdiv_rn(q, hw);
+      const float zhat = __fadd_rn(__fmul_rn(code, hw), hw);           // _scale_and_shift, operation for operation
+      sum = __fadd_rn(sum, __fmul_rn(zhat, basis));
+      bmin = fminf(bmin, 0.5f - fabsf(bounded - q));
+      if (codes) codes[(size_t)(n0 + lane) * D + d] = code;
+    }
+    idx[n0 + lane] = (int32_t)sum;
+    if (boundary) boundary[n0 + lane] = bmin;
+  }
+}
+
 // q[n][c] = b_out[c] + sum_d w_out[c][d] * cb[idx[n]][d]
 template <int D>
 __global__ void __launch_bounds__(256) vq_dequant_kernel(const int32_t* __restrict__ idx, const float* __restrict__ cb,
@@ -383,10 +460,16 @@ __global__ void __launch_bounds__(256) vq_dequant_kernel(const int32_t* __restri
 
 #define VQ_DISPATCH_D(D_, ...)                                          \
   switch (D_) {                                                         \
+    case 1: { constexpr int DD = 1; __VA_ARGS__; } break;               \
+    case 2: { constexpr int DD = 2; __VA_ARGS__; } break;               \
+    case 3: { constexpr int DD = 3; __VA_ARGS__; } break;               \
     case 4: { constexpr int DD = 4; __VA_ARGS__; } break;               \
+    case 5: { constexpr int DD = 5; __VA_ARGS__; } break;               \
+    case 6: { constexpr int DD = 6; __VA_ARGS__; } break;               \
+    case 7: { constexpr int DD = 7; __VA_ARGS__; } break;               \
     case 8: { constexpr int DD = 8; __VA_ARGS__; } break;               \
     case 16: { constexpr int DD = 16; __VA_ARGS__; } break;             \
-    default: return bc::fail(BC_EUNSUPPORTED, "vq: codebook_dim=%d not in {4,8,16}", D_); \
+    default: return bc::fail(BC_EUNSUPPORTED, "vq: codebook_dim=%d not in {1..8,16}", D_); \
   }
 
 extern "C" int bc_vq_encode(const float* z, const float* w_in, const float* b_in, const float* cb_norm, int32_t* idx,
@@ -441,5 +524,27 @@ extern "C" int bc_vq_dequant(const int32_t* idx, const float* cb, const float* w
     vq_dequant_kernel<DD><<<grid, 256, 0, st>>>(idx, cb, w_out, b_out, z_q, residual, bad_count, N, C, Kc, accumulate);
   });
   BC_LAUNCH_CHECK("vq_dequant_kernel");
+  return BC_OK;
+}
+
+extern "C" int bc_fsq_encode(const float* z, const float* w_in, const float* b_in, const float* params5xd, int32_t* idx,
+                             float* codes, float* boundary, int N, int C, int D, bc_stream_t s) {
+  BC_REQUIRE(z && params5xd && idx, "fsq_encode: null pointer");
+  BC_REQUIRE(N > 0 && C > 0 && D > 0, "fsq_encode: bad shape N=%d C=%d D=%d", N, C, D);
+  if (!w_in) BC_REQUIRE(C == D, "fsq_encode: identity projection needs C == D (C=%d D=%d)", C, D);
+  const unsigned grid = (unsigned)((N + VQ_WARPS * FPW - 1) / (VQ_WARPS * FPW));
+  cudaStream_t st = (cudaStream_t)s;
+  switch (D) {
+    case 1: fsq_encode_kernel<1><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 2: fsq_encode_kernel<2><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 3: fsq_encode_kernel<3><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 4: fsq_encode_kernel<4><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 5: fsq_encode_kernel<5><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 6: fsq_encode_kernel<6><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 7: fsq_encode_kernel<7><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    case 8: fsq_encode_kernel<8><<<grid, VQ_WARPS * 32, 0, st>>>(z, w_in, b_in, params5xd, idx, codes, boundary, N, C); break;
+    default: return bc::fail(BC_EUNSUPPORTED, "fsq_encode: %d levels (supported: 1..8)", D);
+  }
+  BC_LAUNCH_CHECK("fsq_encode_kernel");
   return BC_OK;
 }

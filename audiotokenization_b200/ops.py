@@ -440,6 +440,22 @@ def vq_dequant(idx: torch.Tensor, cb: torch.Tensor, w_out: Optional[torch.Tensor
     return z_q
 
 
+def fsq_encode(z: torch.Tensor, w_in: Optional[torch.Tensor], b_in: Optional[torch.Tensor], params: torch.Tensor,
+               want_codes: bool = False, want_boundary: bool = False):
+    """z [N,C] -> (idx int32 [N], codes [N,D] | None, boundary [N] | None); ``params`` = float32 [5,D] (bc_fsq_encode)."""
+    require_cuda(z, "z")
+    z = z if z.is_contiguous() else z.contiguous()
+    N, C = z.shape
+    D = params.shape[1]
+    idx = torch.empty((N,), device=z.device, dtype=torch.int32)
+    codes = torch.empty((N, D), device=z.device, dtype=torch.float32) if want_codes else None
+    boundary = torch.empty((N,), device=z.device, dtype=torch.float32) if want_boundary else None
+    check(load_library().bc_fsq_encode(ptr(z), ptr(w_in), ptr(b_in), ptr(params), ptr(idx), ptr(codes), ptr(boundary),
+                                       N, C, D, stream_ptr(z.device)), "bc_fsq_encode")
+    _count()
+    return idx, codes, boundary
+
+
 def indices_to_int16(idx: torch.Tensor) -> torch.Tensor:
     """int32 [n_q, N] -> int16 [N, n_q] (extract_indices.py:520-532 layout)."""
     require_cuda(idx, "idx")

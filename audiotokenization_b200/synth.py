@@ -147,7 +147,14 @@ def make_decoder_state_dict(cfg: dict, seed: int = 0) -> "OrderedDict[str, torch
     causal, aa = bool(cfg.get("causal", False)), bool(cfg.get("antialias", False))
     cpre = "conv." if causal else ""
     cin, cdim = cfg["in_channels"], cfg["codebook_dim"]
-    for q in range(cfg.get("vq_num_quantizers", 1)):
+    if cfg.get("fsq", False):   # FSQ(levels, dim=in_channels): plain nn.Linear projections, no persistent buffers
+        d = len(cfg["fsq_levels"])
+        # project_in scaled so that the projected latents spread over several quantisation levels
+        sd["quantizer.project_in.weight"] = _uniform(gen, (d, cin), 4.0 / math.sqrt(cin))
+        sd["quantizer.project_in.bias"] = _uniform(gen, (d,), 0.3)
+        sd["quantizer.project_out.weight"] = _uniform(gen, (cin, d), 1.0 / math.sqrt(d))
+        sd["quantizer.project_out.bias"] = _uniform(gen, (cin,), 1.0 / math.sqrt(d))
+    for q in range(0 if cfg.get("fsq", False) else cfg.get("vq_num_quantizers", 1)):
         p = f"quantizer.layers.{q}."
         if cin != cdim:
             _wn_linear(sd, gen, p + "in_proj.", cdim, cin)

@@ -4,6 +4,7 @@ from .codec_encoder import BigCodecEncoder
 from .codec_decoder import BigCodecDecoder
 from .residual_vq import ResidualVQ
 from .factorized_vector_quantize import FactorizedVectorQuantize
+from .finite_scalar_quantization import FSQ
 from .module import (CausalConv1d, CausalConvTranspose1d, DecoderBlock, EncoderBlock, ResidualUnit, ResLSTM,
                      WNConv1d, WNConvTranspose1d, get_precision, precision_scope, set_precision)
 from .activations import SnakeBeta

@@ -15,6 +15,7 @@ from . import activations
 from .alias_free_torch import Activation1d
 from .module import DecoderBlock, ResLSTM, WNConv1d, module_scope
 from .residual_vq import ResidualVQ
+from .finite_scalar_quantization import FSQ
 
 
 class BigCodecDecoder(nn.Module):
@@ -28,13 +29,14 @@ class BigCodecDecoder(nn.Module):
         self.ngf = ngf
         self.up_ratios = up_ratios
         self.fsq = fsq
-        if fsq:
-            raise NotImplementedError("fsq=True (finite scalar quantisation) is outside the hot path: no codec "
-                                      "config enables it (SURVEY.md section 8f rank 3)")
-        self.quantizer = ResidualVQ(num_quantizers=vq_num_quantizers, dim=in_channels, codebook_size=codebook_size,
-                                    codebook_dim=codebook_dim, threshold_ema_dead_code=2,
-                                    commitment=vq_commit_weight, weight_init=vq_weight_init,
-                                    full_commit_loss=vq_full_commit_loss)
+        if fsq:   # vq/codec_decoder.py:41-47
+            self.quantizer = FSQ(levels=fsq_levels, channel_first=True, dim=in_channels)
+            assert codebook_size == np.prod(fsq_levels), "codebook_size must be equal to the product of fsq_levels"
+        else:
+            self.quantizer = ResidualVQ(num_quantizers=vq_num_quantizers, dim=in_channels, codebook_size=codebook_size,
+                                        codebook_dim=codebook_dim, threshold_ema_dead_code=2,
+                                        commitment=vq_commit_weight, weight_init=vq_weight_init,
+                                        full_commit_loss=vq_full_commit_loss)
         channels = upsample_initial_channel
         layers = [WNConv1d(in_channels, channels, kernel_size=7, padding=3, causal=causal)]
         if use_rnn:
@@ -70,7 +72,11 @@ class BigCodecDecoder(nn.Module):
     @torch.no_grad()
     def forward(self, x, vq=True):
         if vq is True:
-            x, q, commit_loss = self.quantizer(x)
+            if self.fsq:   # vq/codec_decoder.py:87-89: (x, int32 indices [B,T], zeros [B])
+                x, q = self.quantizer(x)
+                commit_loss = torch.zeros(x.shape[0], device=x.device)
+            else:
+                x, q, commit_loss = self.quantizer(x)
             return x, q, commit_loss
         return self.decode_cl(ops.to_channels_last(x)).permute(0, 2, 1)
 

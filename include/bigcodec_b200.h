@@ -221,6 +221,19 @@ int bc_vq_dequant(const int32_t* idx, const float* cb, const float* w_out, const
                   float* z_q, float* residual, int* bad_count, int N, int C, int D, int Kc,
                   int accumulate, bc_stream_t s);
 
+/* Finite scalar quantisation, the quantizer BigCodecDecoder selects with fsq=True (vq/codec_decoder.py:41-47,87-89;
+ * FSQ.forward, vq/vector_quantize_pytorch_lucidrains/finite_scalar_quantization.py:111-148,170-175,203-259), eval mode,
+ * one codebook:
+ *   z_e = w_in z + b_in ; bounded = tanh(z_e + shift) * half_l - offset ; q = round-half-even(bounded)
+ *   codes = q / half_width ; idx = int32(sum_j (codes_j * half_width_j + half_width_j) * basis_j)
+ *   z [N][C], w_in [D][C] (+ b_in [D]; NULL, NULL => identity, C == D), params5xd = [5][D] floats:
+ *   half_l | offset | shift | half_width | basis (computed by the host module with the reference's own expressions),
+ *   idx [N] int32, codes [N][D] optional, boundary [N] optional = distance of the closest `bounded` component to a
+ *   rounding boundary (parity tests gate on it).  D = number of levels <= 8.  Dequantisation is bc_vq_dequant with the
+ *   implicit codebook (FSQ._indices_to_codes) as `cb`. */
+int bc_fsq_encode(const float* z, const float* w_in, const float* b_in, const float* params5xd, int32_t* idx,
+                  float* codes, float* boundary, int N, int C, int D, bc_stream_t s);
+
 /* int32 [n_q][N] indices -> int16 [N][n_q], the on-disk layout of extract_indices.py:520-532. */
 int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, int N, bc_stream_t s);
 

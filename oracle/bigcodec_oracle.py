@@ -269,11 +269,46 @@ def vq_layer_forward(sd: SD, prefix: str, z: Tensor) -> Tuple[Tensor, Tensor, Te
     return z_q, idx, torch.zeros(z.shape[0], dtype=dt, device=z.device), margin.view(z.shape[0], -1)
 
 
-def quantize(sd: SD, cfg: dict, z: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """BigCodecDecoder.forward(x, vq=True) -> ResidualVQ.forward (residual_vq.py:21-40).
+def fsq_forward(sd: SD, prefix: str, z: Tensor, levels) -> Tuple[Tensor, Tensor, Tensor]:
+    """FSQ.forward for the decoder's configuration -- FSQ(levels, channel_first=True, dim=C), one codebook, eval
+    (finite_scalar_quantization.py:111-116 bound, :142-148 quantize, :170-175 codes_to_indices, :203-259 forward).
 
-    Returns (z_q [B,C,T'], indices int64 [n_q,B,T'], loss [n_q], margin [n_q,B,T']).
+    Returns (out [B,C,T], indices int32 [B,T], boundary [B,T]) where ``boundary`` is the distance of the closest bounded
+    component to a rounding boundary (0.5 = exactly between two boundaries): the analogue of the VQ cosine margin."""
+    dt = z.dtype
+    lv = torch.tensor(list(levels), dtype=torch.int32, device=z.device)
+    basis = torch.cumprod(torch.tensor([1] + list(levels)[:-1], device=z.device), dim=0, dtype=torch.int32)
+    zt = z.transpose(1, 2)                                              # b n d
+    has_proj = (prefix + "project_in.weight") in sd
+    if has_proj:
+        zt = F.linear(zt, sd[prefix + "project_in.weight"].to(dt), sd[prefix + "project_in.bias"].to(dt))
+    eps = 1e-3
+    half_l = (lv - 1) * (1 + eps) / 2
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    bounded = (zt + shift).tanh() * half_l - offset
+    quantized = bounded.round()
+    half_width = lv // 2
+    codes = quantized / half_width
+    zhat = (codes * half_width) + half_width
+    indices = (zhat * basis).sum(dim=-1).to(torch.int32)
+    boundary = (0.5 - (bounded - quantized).abs()).amin(dim=-1)
+    out = codes.to(dt)
+    if has_proj:
+        out = F.linear(out, sd[prefix + "project_out.weight"].to(dt), sd[prefix + "project_out.bias"].to(dt))
+    return out.transpose(1, 2), indices, boundary
+
+
+def quantize(sd: SD, cfg: dict, z: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """BigCodecDecoder.forward(x, vq=True) -> ResidualVQ.forward (residual_vq.py:21-40), or, with ``fsq``, FSQ.forward
+    (vq/codec_decoder.py:87-89).
+
+    Returns (z_q [B,C,T'], indices int64 [n_q,B,T'], loss [n_q], margin [n_q,B,T']); with ``fsq``: indices int32
+    [B,T'] (the reference's shape), loss [B] zeros, margin = boundary distance [B,T'].
     """
+    if cfg.get("fsq", False):
+        out, idx, boundary = fsq_forward(sd, "quantizer.", z, cfg["fsq_levels"])
+        return out, idx, torch.zeros(z.shape[0], dtype=z.dtype, device=z.device), boundary
     out = torch.zeros_like(z)
     residual = z
     all_idx, all_loss, all_margin = [], [], []

@@ -48,6 +48,7 @@ CASES = [
     ("debug_nodil_1s", "debug_nodil", False, 16000, 1, "tones"),
     ("config9_base_1s", "config9_base", False, 16000, 1, "tones"),
     ("default_half_s", "default", False, 8000, 1, "tones"),   # original BigCodec: ngf 48, 1024-d, channels 48..1536
+    ("tiny_fsq", "tiny_fsq", False, 4000, 2, "tones"),        # the decoder's FSQ quantizer branch (fsq=True)
 ]
 
 
@@ -79,15 +80,24 @@ def main():
                 z = enc(x.to(dt))
                 z_q, idx, loss = dec(z, vq=True)
                 y = dec(z_q, vq=False)
-                # the int -> embedding entry (vq2emb is channel-last, residual_vq.py:42-48)
-                emb = dec.vq2emb(idx.permute(1, 2, 0))
-                # cosine margins from the reference's own quantizer parameters
-                layer = dec.quantizer.layers[0]
-                z_e = layer.in_proj(z.transpose(1, 2))
-                e = torch.nn.functional.normalize(z_e.reshape(-1, z_e.shape[-1]))
-                c = torch.nn.functional.normalize(layer.codebook.weight)
-                top2 = (e @ c.t()).topk(2, dim=1).values
-                margin = (top2[:, 0] - top2[:, 1]).view(z.shape[0], -1)
+                if cfg["codec_decoder"].get("fsq", False):
+                    # FSQ: indices int32 [B,T']; the index -> embedding entry is indices_to_codes (channel-first), and the
+                    # analogue of the cosine margin is the distance of the bounded latents to the nearest rounding boundary
+                    q = dec.quantizer
+                    emb = (q.indices_to_codes(idx).transpose(1, 2) if dt == torch.float32 else
+                           q.project_out(q._indices_to_codes(idx).to(dt)))        # the reference's own method is float32-only
+                    bounded = q.bound(q.project_in(z.transpose(1, 2)))
+                    margin = (0.5 - (bounded - bounded.round()).abs()).amin(dim=-1)
+                else:
+                    # the int -> embedding entry (vq2emb is channel-last, residual_vq.py:42-48)
+                    emb = dec.vq2emb(idx.permute(1, 2, 0))
+                    # cosine margins from the reference's own quantizer parameters
+                    layer = dec.quantizer.layers[0]
+                    z_e = layer.in_proj(z.transpose(1, 2))
+                    e = torch.nn.functional.normalize(z_e.reshape(-1, z_e.shape[-1]))
+                    c = torch.nn.functional.normalize(layer.codebook.weight)
+                    top2 = (e @ c.t()).topk(2, dim=1).values
+                    margin = (top2[:, 0] - top2[:, 1]).view(z.shape[0], -1)
             out[f"z_{tag}"] = z.to(torch.float32).numpy()
             out[f"zq_{tag}"] = z_q.to(torch.float32).numpy()
             out[f"idx_{tag}"] = idx.numpy().astype(np.int32)

@@ -114,3 +114,33 @@ def test_single_pass_bf16_fast_mode_is_within_its_documented_envelope(case):
     assert e_z <= 5e-2, e_z
     assert agree >= 0.85, agree
     print(f"{case} bf16: z rel {e_z:.2e}, idx agree {agree:.4f}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_fsq_decoder_branch_round_trip_matches_reference_fixture(precision):
+    """BigCodecDecoder(fsq=True) (vq/codec_decoder.py:41-47,87-89) end to end against the live-reference fixture:
+    int32 indices [B, T'] exact away from rounding boundaries, (x, q, zeros[B]) return convention, waveform, the
+    driver-level index path (int16 (T', 1) arrays)."""
+    g = load_golden("tiny_fsq")
+    cfg = configs.get_config(g["cfg_name"], antialias=g["antialias"])
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=g["seed"])
+    model = BigCodecModel(cfg, enc_sd, dec_sd, device="cuda", precision=precision)
+    x = synth.synth_batch(0, g["batch"], g["num_samples"], g["kind"]).cuda()
+    z = model.encoder(x)
+    assert rel(z.cpu().numpy(), g["z_f64"]) <= 2e-4
+    z_q, idx, loss = model.decoder(z, vq=True)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == g["idx_f32"].shape and tuple(loss.shape) == (g["batch"],)
+    assert float(loss.abs().sum()) == 0.0
+    decided = g["margin_f64"] > (1e-5 if precision == "fp32" else 2e-3)     # boundary distance of the bounded latents
+    assert np.array_equal(idx.cpu().numpy()[decided], g["idx_f64"][decided])
+    same = idx.cpu().numpy() == g["idx_f32"]
+    assert same.mean() >= 0.98
+    assert rel(z_q.cpu().numpy().transpose(0, 2, 1)[same], g["zq_f32"].transpose(0, 2, 1)[same]) <= 1e-5
+    y = model.decoder(torch.from_numpy(g["zq_f32"]).cuda(), vq=False)
+    assert rel(y.cpu().numpy(), g["y_f32"]) <= 2e-4
+    out = model(x, round_trip=True)
+    assert np.array_equal(out["indices"].cpu().numpy(), idx.cpu().numpy())
+    emb = model.decoder.quantizer.indices_to_codes(idx)
+    assert rel(emb.cpu().numpy().transpose(0, 2, 1)[same], g["emb_f32"][same]) <= 1e-5
+    i16 = model.extract_indices(x.cpu().pin_memory(), micro_batch=2)
+    assert i16.shape == (g["batch"], g["idx_f32"].shape[1], 1) and np.array_equal(i16[:, :, 0], idx.cpu().numpy().astype(np.int16))

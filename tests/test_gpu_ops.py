@@ -599,3 +599,38 @@ def test_stream_residual_unit_matches_oracle(precision, tol, C, dil, causal, B, 
     assert got.shape == want.shape
     assert rel(got, want) <= tol
     assert rel(got, other) <= tol
+
+
+@pytest.mark.parametrize("levels,C,B,T", [([4, 4, 4, 8], 64, 2, 500), ([8, 5, 5, 5], 512, 3, 257), ([7, 5, 5, 5, 5], 96, 1, 1000),
+                                          ([3], 32, 2, 33), ([8, 8, 8, 6, 5], 1024, 1, 130), ([2, 2], 2, 2, 64)])
+def test_fsq_quantizer_matches_oracle(levels, C, B, T):
+    """bc_fsq_encode + dequantisation over the implicit codebook against the oracle restatement of FSQ.forward
+    (finite_scalar_quantization.py:203-259): indices bit-exact wherever no bounded component lies within 1e-5 of a
+    rounding boundary (tanhf differs from the CPU library's tanh in the last ulp), outputs to float32 rounding;
+    indices_to_codes round trip; odd and even level counts, identity projection (dim == number of levels)."""
+    from audiotokenization_b200.vq import FSQ
+    g = gen(sum(levels) + C + T)
+    q = FSQ(levels, dim=C, channel_first=True)
+    sd = {}
+    if q.has_projections:
+        q.project_in.weight.data = torch.randn(len(levels), C, generator=g) * (3.0 / C ** 0.5)
+        q.project_in.bias.data = torch.randn(len(levels), generator=g) * 0.3
+        sd = {"q." + k: v.data.clone() for k, v in q.named_parameters()}
+    z = torch.randn(B, C, T, generator=g) * (1.5 if q.has_projections else 2.0)
+    want, widx, wbound = oracle.fsq_forward(sd, "q.", z, levels)
+    q = q.to(DEV)
+    out, idx = q(z.to(DEV))
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (B, T) and tuple(out.shape) == (B, C, T)
+    _, _, bound = q.encode_cl(ops.to_channels_last(z.to(DEV)), want_boundary=True)
+    tol = 1e-5 * max(1.0, C / 256)            # the C-term projection sums in another order than the CPU library's GEMM
+    decided = wbound > tol
+    assert float(decided.float().mean()) > 0.99
+    assert torch.equal(idx.cpu()[decided], widx[decided])
+    assert float((bound.cpu() - wbound).abs().max()) <= tol
+    same = (idx.cpu() == widx)
+    assert rel(out.cpu().permute(0, 2, 1)[same], want.permute(0, 2, 1)[same]) <= 1e-6
+    assert len(torch.unique(idx)) > min(q.codebook_size, B * T) // 8
+    back = q.indices_to_codes(idx)
+    assert torch.equal(back, out)
+    with pytest.raises(IndexError):
+        q.indices_to_codes(torch.full((1, 4), q.codebook_size, dtype=torch.int32, device=DEV))

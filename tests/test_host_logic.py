@@ -16,7 +16,7 @@ from audiotokenization_b200.vq import module as M
 from oracle import bigcodec_oracle as oracle
 
 
-@pytest.mark.parametrize("name", ["tiny", "base", "debug", "debug_causal", "config9_base", "default"])
+@pytest.mark.parametrize("name", ["tiny", "base", "debug", "debug_causal", "config9_base", "default", "tiny_fsq"])
 @pytest.mark.parametrize("aa", [False, True])
 def test_state_dict_keys_and_shapes_match_reference_layout(name, aa):
     cfg = configs.get_config(name, antialias=aa)
@@ -109,8 +109,15 @@ def test_unsupported_configurations_are_errors():
     with pytest.raises(NotImplementedError):
         M.ResLSTM(32, bidirectional=True)
     cfg = configs.get_config("tiny")["codec_decoder"]
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):          # vq/codec_decoder.py:47: codebook_size must equal prod(fsq_levels)
         BigCodecDecoder(**dict(cfg, fsq=True, codebook_size=128))
+    from audiotokenization_b200.vq import FSQ
+    with pytest.raises(NotImplementedError):
+        FSQ([4, 4], num_codebooks=2)
+    q = BigCodecDecoder(**dict(cfg, fsq=True, fsq_levels=[8, 5, 5], codebook_size=200)).quantizer
+    assert q.codebook_size == 200 and tuple(q.implicit_codebook.shape) == (200, 3)
+    assert q._basis.tolist() == [1, 8, 40] and sorted(k for k, _ in q.named_parameters()) == [
+        "project_in.bias", "project_in.weight", "project_out.bias", "project_out.weight"]
     with pytest.raises(ValueError):
         M.set_precision("fp8")
 

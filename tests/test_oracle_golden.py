@@ -71,3 +71,22 @@ def test_int16_disk_form():
     idx = torch.arange(7).view(1, 1, 7)
     arr = oracle.indices_to_int16(idx)
     assert arr.dtype == np.int16 and arr.shape == (7, 1)
+
+
+def test_oracle_fsq_branch_matches_reference_fixture():
+    """BigCodecDecoder(fsq=True): the oracle's FSQ restatement against the live reference (fixture tiny_fsq): int32
+    indices of shape [B, T'], bit-exact; quantised latents / waveform to float32 rounding; boundary distances."""
+    g = load_golden("tiny_fsq")
+    cfg = configs.get_config(g["cfg_name"], antialias=g["antialias"])
+    assert cfg["codec_decoder"]["fsq"] is True
+    enc_sd, dec_sd = synth.make_state_dicts(cfg, seed=g["seed"])
+    x = synth.synth_batch(0, g["batch"], g["num_samples"], g["kind"])
+    out = oracle.round_trip(enc_sd, dec_sd, cfg, x)
+    assert out["indices"].dtype == torch.int32 and tuple(out["indices"].shape) == g["idx_f32"].shape == (2, 100)
+    assert np.array_equal(out["indices"].numpy(), g["idx_f32"])
+    assert rel(out["z_q"].numpy(), g["zq_f32"]) <= 2e-6 and rel(out["x_rec"].numpy(), g["y_f32"]) <= 2e-6
+    assert np.abs(out["margin"].numpy() - g["margin_f32"]).max() <= 1e-5      # bounded latents reach |3.5|: float32 rounding of z
+    # every level combination decodes back through the implicit codebook (random latents reach many more codes)
+    z = torch.randn(3, 64, 500, generator=torch.Generator().manual_seed(4)) * 3
+    q, idx, _, _ = oracle.quantize(dec_sd, cfg["codec_decoder"], z)
+    assert len(torch.unique(idx)) > 150 and int(idx.min()) >= 0 and int(idx.max()) < 512
