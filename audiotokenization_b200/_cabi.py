@@ -49,6 +49,12 @@ _SIGNATURES = {
     "bc_vq_encode": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "bc_fsq_encode": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),
+    "bc_ipc_alloc": (c_int, [POINTER(c_void_p), c_size_t]),
+    "bc_ipc_free": (c_int, [c_void_p]),
+    "bc_ipc_export": (c_int, [c_void_p, c_char_p]),
+    "bc_ipc_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "bc_ipc_close": (c_int, [c_void_p]),
+    "bc_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "bc_code_histogram": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
     "bc_code_entropy": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "bc_debug_set_ru_trace": (c_int, [c_void_p]),

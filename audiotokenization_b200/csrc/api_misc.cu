@@ -126,3 +126,37 @@ extern "C" int bc_indices_to_int16(const int32_t* idx, int16_t* out, int n_q, in
   BC_LAUNCH_CHECK("idx_to_i16_kernel");
   return BC_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Peer memory for the one ordered hand-off of the long-form path (the conv front end of ONE long
+// recording is dealt out over the GPUs chunk by chunk; each owner then stores its frame-rate features straight into the
+// LSTM owner's buffer over NVLink -- plain peer stores, not a collective, no NCCL).  One process per GPU, so the
+// buffer crosses processes as a CUDA IPC handle.
+// ---------------------------------------------------------------------------
+extern "C" int bc_ipc_alloc(void** dev_ptr, size_t bytes) {
+  BC_REQUIRE(dev_ptr && bytes > 0, "ipc_alloc: bad arguments");
+  return bc::cuda_check(cudaMalloc(dev_ptr, bytes), "cudaMalloc(ipc)");
+}
+extern "C" int bc_ipc_free(void* dev_ptr) { return bc::cuda_check(cudaFree(dev_ptr), "cudaFree(ipc)"); }
+extern "C" int bc_ipc_export(const void* dev_ptr, unsigned char* handle64) {
+  BC_REQUIRE(dev_ptr && handle64, "ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr));
+  if (e != cudaSuccess) return bc::cuda_check(e, "cudaIpcGetMemHandle");
+  memcpy(handle64, &h, 64);
+  return BC_OK;
+}
+extern "C" int bc_ipc_open(const unsigned char* handle64, void** peer_ptr) {
+  BC_REQUIRE(handle64 && peer_ptr, "ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  return bc::cuda_check(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+extern "C" int bc_ipc_close(void* peer_ptr) { return bc::cuda_check(cudaIpcCloseMemHandle(peer_ptr), "cudaIpcCloseMemHandle"); }
+// dst / src: any two device pointers valid in this process (local, or a peer buffer opened with bc_ipc_open)
+extern "C" int bc_peer_copy(void* dst, const void* src, size_t bytes, bc_stream_t s) {
+  BC_REQUIRE(dst && src, "peer_copy: null pointer");
+  if (bytes == 0) return BC_OK;
+  return bc::cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)s), "cudaMemcpyAsync(peer)");
+}

@@ -248,6 +248,21 @@ int bc_code_histogram(const int32_t* idx, long long N, int Kc, unsigned long lon
  * :66-69, before the division), out3[2] = sum(counts).  out3: 3 doubles, DEVICE. */
 int bc_code_entropy(const unsigned long long* counts, int Kc, double* out3, bc_stream_t s);
 
+/* ---- peer memory for the long-form hand-off ----------------------------------------------
+ * BASELINE configs[3] on several GPUs: the conv front end of ONE recording is sharded by chunk, then the frame-rate
+ * features (2 KB per frame) make one ordered hand-off to the GPU that runs the sequential LSTM + VQ.  The reference has
+ * no multi-GPU inference path at all; SURVEY prescribes peer copies over NVLink, not a collective.  One process per GPU:
+ * the owner allocates the receive buffer (bc_ipc_alloc: plain cudaMalloc, exportable), publishes its 64-byte IPC handle
+ * (bc_ipc_export; the handle travels over the host-side process group), peers map it (bc_ipc_open, peer access enabled
+ * lazily) and store their rows with bc_peer_copy (cudaMemcpyAsync on the caller's stream).  Completion is the callers'
+ * business (stream synchronise + host barrier). */
+int bc_ipc_alloc(void** dev_ptr, size_t bytes);
+int bc_ipc_free(void* dev_ptr);
+int bc_ipc_export(const void* dev_ptr, unsigned char* handle64);
+int bc_ipc_open(const unsigned char* handle64, void** peer_ptr);
+int bc_ipc_close(void* peer_ptr);
+int bc_peer_copy(void* dst, const void* src, size_t bytes, bc_stream_t s);
+
 /* debug only: per-stage clock64 stamps of the persistent ResidualUnit kernel (CTA 0, first 64 tiles) */
 int bc_debug_set_ru_trace(void* device_buffer);
 /* same for the streamed-weight kernel (events: producer, MMA, MID, store stamps and MMA-warp wait totals) */
