@@ -11,6 +11,7 @@
 // 8 x (BN/8) register tile; input channels are consumed in chunks of 16 through a
 // shared-memory slab holding every input row the tile's taps touch.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -320,6 +321,69 @@ __global__ void __launch_bounds__(TAIL_TT) tail_conv_kernel(const float* __restr
   y[(size_t)b * T_out + t] = acc;
 }
 
+// tail, warp-per-block form (C_in <= 32, the codec's C -> 1 waveform conv): a warp produces 32 consecutive outputs; lane c
+// owns input channel c and its K weights, walks the 32 + K - 1 input rows of the block (one coalesced 128-byte row per
+// load), applies SnakeBeta ONCE per element and adds w[k][c] * s to the (at most K) outputs the row feeds -- 32 partial
+// sums in registers, all indices compile-time.  A 31-shuffle transposing reduction then leaves output j in lane j, so the
+// block leaves as one coalesced 128-byte store.  ~22 warp-instructions per output (the staged kernel above: ~53).
+// SnakeBeta uses the range-reduced SFU sine of the tensor-core kernels (|error| ~ 4e-7 absolute).
+template <int K>
+__global__ void __launch_bounds__(256) tail_conv_warp_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ sa,
+                                                             const float* __restrict__ sib, float* __restrict__ y, int T_in,
+                                                             int T_out, int C_in, int pad_left, int flags, int blocks_per_item,
+                                                             long long total_blocks) {
+  const int lane = threadIdx.x & 31;
+  const long long wb = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wb >= total_blocks) return;
+  const int b = (int)(wb / blocks_per_item);
+  const int tb = (int)(wb - (long long)b * blocks_per_item) * 32;
+  const bool ch_ok = lane < C_in;
+  const bool snake = (flags & BC_CONV_SNAKE_IN) != 0;
+  float wk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wk[k] = ch_ok ? __ldg(w + k * C_in + lane) : 0.f;
+  const float a = (snake && ch_ok) ? __ldg(sa + lane) : 0.f, ib = (snake && ch_ok) ? __ldg(sib + lane) : 0.f;
+  const float* xb = x + (size_t)b * T_in * C_in + lane;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  // rows r = tb - pad_left + i, i in [0, 32 + K - 1): row i feeds output j = i - k through tap k
+  constexpr int ROWS = 32 + K - 1;
+  float xv[ROWS];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int g = tb - pad_left + i;
+    xv[i] = (ch_ok && g >= 0 && g < T_in) ? __ldg(xb + (size_t)g * C_in) : 0.f;     // zero padding AFTER the activation: snake(0) = 0
+  }
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const float sv = snake ? bc::tc::snake_tc(xv[i], a, ib) : xv[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = i - k;
+      if (j >= 0 && j < 32) acc[j] = fmaf(wk[k], sv, acc[j]);
+    }
+  }
+  // transposing reduction: after the step with offset o, a lane keeps the partial sums of the outputs whose bit o equals its own
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? acc[i] : acc[i + o];
+      const float keep = up ? acc[i + o] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  const int t = tb + lane;
+  if (t < T_out) {
+    float v = acc[0] + (bias ? __ldg(bias) : 0.f);
+    if (flags & BC_CONV_TANH_OUT) v = tanhf(v);
+    y[(size_t)b * T_out + t] = v;
+  }
+}
+
 template <int BN>
 int launch(const ConvParams& p, cudaStream_t st) {
   const size_t smem = ((size_t)p.slab_rows * CKP + (size_t)p.K * CK * BN) * sizeof(float) + 16;
@@ -383,6 +447,16 @@ extern "C" int bc_conv1d_fwd(const float* x, const float* w, const float* bias, 
     else if (K == 3) stem_conv_kernel<3><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
     else stem_conv_kernel<1><<<blocks, 256, 0, st_>>>(x, w, bias, y, T_in, T_out, C_out, pad_left, total);
     BC_LAUNCH_CHECK("stem_conv_kernel");
+    return BC_OK;
+  }
+  if (C_out == 1 && stride == 1 && dilation == 1 && !res && y_tstride == 1 && y_toffset == 0 && y_rows == T_out && K == 7 &&
+      C_in <= 32 && C_in >= 8) {
+    const int blocks_per_item = (T_out + 31) / 32;
+    const long long total_blocks = (long long)blocks_per_item * B;
+    const unsigned grid = (unsigned)((total_blocks + 7) / 8);
+    tail_conv_warp_kernel<7><<<grid, 256, 0, st_>>>(x, w, bias, snake_a, snake_ib, y, T_in, T_out, C_in, pad_left, flags,
+                                                   blocks_per_item, total_blocks);
+    BC_LAUNCH_CHECK("tail_conv_warp_kernel");
     return BC_OK;
   }
   if (C_out == 1 && stride == 1 && dilation == 1 && !res && y_tstride == 1 && y_toffset == 0 && y_rows == T_out &&

@@ -110,6 +110,7 @@ struct SParams {
   const float* sa2;
   const float* sib2;
   int B, T_in, T_out, C_in, C_out, K, stride, dil, pad_left, flags;
+  int nt_shift;     // n-tiles >= nt_shift read their taps one row later (pad_left - 1): the q = 1 phases of a transposed conv
   int N, groups, tpu, upg, gpu1;
   int slab_rows, rpp, NA, NB, acc_stages, acc_stride, epi_warps;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     for (int tile = first; tile < p.total_tiles; tile += step, ++it, tp.advance(step, p.tiles_per_item, p.B)) {
       const int b = tp.b;
       const int t0 = tp.tt * BM;
-      const int g0row = t0 * p.stride - p.pad_left;
+      const int g0row = t0 * p.stride - p.pad_left + (tp.nt >= p.nt_shift ? 1 : 0);
       const float* xb = p.x + (size_t)b * p.T_in * p.C_in + c4 * 4;
       long long wE = 0;
       for (int g = 0; g < p.groups; ++g, ++sq) {
@@ -705,7 +706,10 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   if (C_in % 16 != 0 || C_in < 32 || K < 1 || K > 32 || stride < 1 || dilation < 1) return false;
   if (stride > 1 && dilation > 1) return false;
   int N = 0;
-  if (C_out <= 256) N = C_out; else if (C_out % 256 == 0) N = 256;
+  if (C_out <= 256 && (C_out & (C_out - 1)) == 0) N = C_out;
+  else if (C_out % 256 == 0) N = 256;
+  else if (C_out % 128 == 0) N = 128;      // e.g. the 5 x 128 channel blocks of a 256 -> 128 stride-5 transposed conv
+  else if (C_out % 64 == 0) N = 64;
   if (N < 64 || N % 32 != 0 || (N & (N - 1)) != 0) return false;   // 64, 128, 256
   if (fused && (C_in != C_out || N != C_out || stride != 1 || N % A2_CH != 0)) return false;
   const int split = precision == BC_PREC_BF16X3 ? 2 : 1;
@@ -841,7 +845,35 @@ extern "C" int bc_conv1d_stream_fwd(const float* x, const void* w_image, const f
   p.x = x; p.y = y; p.res = res; p.w7 = reinterpret_cast<const uint8_t*>(w_image); p.w1 = nullptr;
   p.bias = bias; p.bias2 = nullptr; p.sa1 = snake_a; p.sib1 = snake_ib; p.sa2 = nullptr; p.sib2 = nullptr;
   p.B = B; p.T_in = T_in; p.T_out = T_out; p.C_in = C_in; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;
-  p.pad_left = pad_left; p.flags = flags;
+  p.pad_left = pad_left; p.flags = flags; p.nt_shift = 0x7fffffff;
+  return launch_stream(p, pl, 0, (cudaStream_t)s);
+}
+
+// Transposed conv (k = 2*stride, T_out = T_in*stride; vq/module.py:67-72,119-136) as ONE launch of the streamed-weight
+// kernel: output phase ph of row m is  W[j0+stride]^T x[m+q-1] + W[j0]^T x[m+q]  with j0 = (ph+padding) % stride,
+// q = (ph+padding) / stride, so all phases together are a 2-tap conv with stride*C_out output channels whose output
+// [B][T_in][stride*C_out] IS y [B][T_in*stride][C_out]; the n-tiles of the q = 1 phases read their taps one row later.
+// w_image: pack_stream_weight of [2][C_in][stride*C_out] (column ph*C_out + co = phase filter ph), bias_tiled:
+// [stride*C_out].  Needs C_out % n_tile == 0 (every n-tile inside one phase); other geometries use the K = 3 zero-padded
+// form through bc_conv1d_stream_fwd or the per-phase path of bc_convtr1d_fwd.
+extern "C" int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                                      const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                                      int padding, int flags, int precision, bc_stream_t s) {
+  BC_REQUIRE(x && w_image && y, "convtr1d(stream): null pointer");
+  BC_REQUIRE(B > 0 && T_in > 0 && stride >= 2 && padding >= 0 && padding < stride, "convtr1d(stream): bad shape B=%d T_in=%d stride=%d padding=%d", B, T_in, stride, padding);
+  BC_REQUIRE(!(flags & BC_CONV_SNAKE_IN) || (snake_a && snake_ib), "convtr1d(stream): BC_CONV_SNAKE_IN needs snake_a and snake_ib");
+  StreamPlan pl;
+  if (!stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl) || C_out % pl.N != 0)
+    return bc::fail(BC_EUNSUPPORTED, "convtr1d(stream): C_in=%d C_out=%d stride=%d has no single-launch plan", C_in, C_out, stride);
+  BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w_image) && bc::aligned16(y) && (!bias_tiled || bc::aligned16(bias_tiled)) &&
+                 (!snake_a || bc::aligned16(snake_a)) && (!snake_ib || bc::aligned16(snake_ib)),
+             "convtr1d(stream): pointers must be 16-byte aligned");
+  SParams p{};
+  p.x = x; p.y = y; p.res = nullptr; p.w7 = reinterpret_cast<const uint8_t*>(w_image); p.w1 = nullptr;
+  p.bias = bias_tiled; p.bias2 = nullptr; p.sa1 = snake_a; p.sib1 = snake_ib; p.sa2 = nullptr; p.sib2 = nullptr;
+  p.B = B; p.T_in = T_in; p.T_out = T_in; p.C_in = C_in; p.C_out = stride * C_out; p.K = 2; p.stride = 1; p.dil = 1;
+  p.pad_left = 1; p.flags = flags;
+  p.nt_shift = (stride - padding) * (C_out / pl.N);          // first n-tile of phase ph = stride - padding, the first with q = 1
   return launch_stream(p, pl, 0, (cudaStream_t)s);
 }
 
@@ -862,7 +894,7 @@ extern "C" int bc_resunit_stream_fwd(const float* x, const void* w7_image, const
   p.x = x; p.y = y; p.res = x; p.w7 = reinterpret_cast<const uint8_t*>(w7_image); p.w1 = reinterpret_cast<const uint8_t*>(w1_image);
   p.bias = b7; p.bias2 = b1; p.sa1 = snake1_a; p.sib1 = snake1_ib; p.sa2 = snake2_a; p.sib2 = snake2_ib;
   p.B = B; p.T_in = T; p.T_out = T; p.C_in = C; p.C_out = C; p.K = K; p.stride = 1; p.dil = dilation;
-  p.pad_left = pad_left; p.flags = BC_CONV_SNAKE_IN;
+  p.pad_left = pad_left; p.flags = BC_CONV_SNAKE_IN; p.nt_shift = 0x7fffffff;
   return launch_stream(p, pl, 1, (cudaStream_t)s);
 }
 

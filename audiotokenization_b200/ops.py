@@ -181,6 +181,45 @@ def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[tor
     return y
 
 
+def conv_transpose1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias_tiled: Optional[torch.Tensor], *, stride: int,
+                            padding: int, c_out: int, three_tap: bool, snake_a: Optional[torch.Tensor] = None,
+                            snake_ib: Optional[torch.Tensor] = None, precision: str) -> torch.Tensor:
+    """Transposed conv (k = 2*stride) as ONE launch of the persistent streamed-weight kernel: all output phases are the
+    channel blocks of a conv with stride*C_out outputs (``pack_convtr_stream_weight``)."""
+    x = _cl(x)
+    B, T_in, C_in = x.shape
+    y = torch.empty((B, T_in, stride * c_out), device=x.device, dtype=torch.float32)
+    flags = BC_CONV_SNAKE_IN if snake_a is not None else 0
+    with _Timed(("convtr1d", C_in, c_out, 2 * stride, stride, 1, T_in * stride, B, precision),
+                2.0 * B * T_in * stride * c_out * C_in * 2, x.device, "conv_stream_kernel", 4.0 * B * T_in * (C_in + stride * c_out)):
+        if three_tap:
+            check(load_library().bc_conv1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), None,
+                                                      ptr(y), B, T_in, C_in, T_in, stride * c_out, 3, 1, 1, 1, flags,
+                                                      PRECISIONS[precision], stream_ptr(x.device)), "bc_conv1d_stream_fwd")
+        else:
+            check(load_library().bc_convtr1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), ptr(y),
+                                                        B, T_in, C_in, c_out, stride, padding, flags, PRECISIONS[precision],
+                                                        stream_ptr(x.device)), "bc_convtr1d_stream_fwd")
+    _count()
+    return y.view(B, T_in * stride, c_out)
+
+
+def pack_convtr_stream_weight(w_phases: torch.Tensor, stride: int, padding: int, n_tile: int, precision: str):
+    """fp32 phase filters [stride, 2, C_in, C_out] -> (streamed-weight image, three_tap).  Two taps when every n-tile
+    lies inside one phase (the kernel shifts the taps of the q = 1 phases by one row); otherwise three taps on rows
+    m-1, m, m+1 with zeros where a phase does not reach (q = 0: taps 0, 1; q = 1: taps 1, 2)."""
+    s, two, c_in, c_out = w_phases.shape
+    three_tap = c_out % n_tile != 0
+    if not three_tap:
+        w = w_phases.permute(1, 2, 0, 3).reshape(2, c_in, s * c_out)
+    else:
+        w = torch.zeros((3, c_in, s * c_out), dtype=w_phases.dtype, device=w_phases.device)
+        for ph in range(s):
+            q = (ph + padding) // s
+            w[q:q + 2, :, ph * c_out:(ph + 1) * c_out] = w_phases[ph]
+    return pack_stream_weight(w.contiguous(), n_tile, precision), three_tap
+
+
 _TC_PLANS = {}
 
 

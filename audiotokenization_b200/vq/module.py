@@ -25,6 +25,7 @@ _PRECISION = ["fp32"]
 LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
+CONVTR_STREAM = [True]  # ... and transposed convs as ONE launch of it (all phases as channel blocks)
 import os as _os
 STREAM_MIN_CIN = [int(_os.environ.get("BC_STREAM_MIN_CIN", "32"))]    # ... when the layer has at least this many input channels
 STREAM_RU_MIN_C = [int(_os.environ.get("BC_STREAM_RU_MIN_C", "128"))]  # ... ResidualUnits: narrower ones keep their weights resident (ru_persist)
@@ -233,11 +234,36 @@ class _ConvTranspose1dWN(_WNParams):
                                                  for ph in range(self.stride)]).contiguous())
         return cache["w"], b, precision
 
+    def stream_image(self, precision: str):
+        """(image, tiled bias, three_tap) for the single-launch streamed-weight form, or None when the geometry has no
+        plan (narrow / irregular layers keep the per-phase path)."""
+        nt = _stream_tile(self.in_channels, self.stride * self.out_channels, 2, 1, 1, precision)
+        if nt is None:
+            return None
+        if self.out_channels % nt != 0:       # n-tiles straddle phases: three-tap zero-padded form needs its own plan
+            nt = _stream_tile(self.in_channels, self.stride * self.out_channels, 3, 1, 1, precision)
+            if nt is None:
+                return None
+        cache = self.__dict__.setdefault("_stream_cache", {})
+        key = (precision, nt, self._key())
+        if cache.get("key") != key:
+            w, b = self.packed()
+            img, three = ops.pack_convtr_stream_weight(w, self.stride, self.padding, nt, precision)
+            cache.clear()
+            cache.update(key=key, w=img, b=b.repeat(self.stride).contiguous(), three=three)
+        return cache["w"], cache["b"], cache["three"]
+
     def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None):
-        w, b, prec = self.packed_for(get_precision())
+        precision = get_precision()
         a = ib = None
         if act is not None:
             a, ib = act.device_params()
+        st = self.stream_image(precision) if CONVTR_STREAM[0] else None
+        if st is not None:
+            return ops.conv_transpose1d_stream(x_cl, st[0], st[1], stride=self.stride, padding=self.padding,
+                                               c_out=self.out_channels, three_tap=st[2], snake_a=a, snake_ib=ib,
+                                               precision=precision)
+        w, b, prec = self.packed_for(precision)
         return ops.conv_transpose1d(x_cl, w, b, stride=self.stride, padding=self.padding, snake_a=a, snake_ib=ib,
                                     precision=prec, c_out=self.out_channels)
 

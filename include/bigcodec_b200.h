@@ -161,6 +161,17 @@ int bc_convtr1d_fwd(const float* x, const float* w_phases, const float* bias,
                     int B, int T_in, int C_in, int C_out, int stride, int padding, int flags,
                     int precision, bc_stream_t s);
 
+/* The same transposed conv as ONE launch of the streamed-weight kernel (tensor-core modes): all phases together are a
+ * 2-tap conv with stride*C_out output channels whose output [B][T_in][stride*C_out] is y [B][T_in*stride][C_out]; n-tiles
+ * of the phases with (ph+padding)/stride = 1 read their taps one row later.  w_image = the bc_conv1d_stream_fwd image
+ * of [2][C_in][stride*C_out] (column ph*C_out + co = phase filter ph, taps as in w_phases), n_tile from
+ * bc_stream_plan(C_in, stride*C_out, 2, 1, 1, ...); bias_tiled [stride*C_out] = bias repeated per phase.  Needs
+ * C_out % n_tile == 0, else BC_EUNSUPPORTED (narrower layers: the 3-tap zero-padded form through
+ * bc_conv1d_stream_fwd, or bc_convtr1d_fwd). */
+int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                           const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                           int padding, int flags, int precision, bc_stream_t s);
+
 /* ---- LSTM ---------------------------------------------------------------- */
 /* One uni-directional LSTM layer, recurrent part (nn.LSTM inside ResLSTM,
  * vq/module.py:143-167; gate order i,f,g,o; h0 = c0 = 0).

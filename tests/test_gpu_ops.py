@@ -333,24 +333,43 @@ def test_edge_convs_stay_on_fp32_kernel_in_tensor_core_modes(precision):
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 3e-5), ("bf16", 1e-2)])
-@pytest.mark.parametrize("cin,cout,stride,T", [(64, 32, 2, 501), (128, 64, 4, 250), (512, 256, 5, 80)])
-def test_conv_transpose1d_tensor_core_modes(precision, tol, cin, cout, stride, T):
+@pytest.mark.parametrize("cin,cout,stride,causal,T", [(64, 32, 2, False, 501), (128, 64, 4, False, 250), (512, 256, 5, False, 80),
+                                                      (256, 128, 5, False, 1000), (128, 64, 4, True, 300), (64, 32, 2, True, 129),
+                                                      (256, 128, 2, False, 77), (96, 48, 3, False, 200)])
+def test_conv_transpose1d_tensor_core_modes(precision, tol, cin, cout, stride, causal, T):
+    """Single-launch form on the streamed-weight kernel (all phases as channel blocks of one 2-tap conv, q = 1 phases
+    shifted per n-tile; three zero-padded taps when an n-tile straddles phases, e.g. 64 -> 32), the causal variant, and
+    agreement with the per-phase path."""
     g = gen(cin + cout + stride + T)
-    m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, padding=stride // 2 + stride % 2,
-                            output_padding=stride % 2)
+    if causal:
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, causal=True)
+        inner = m.conv
+    else:
+        m = M.WNConvTranspose1d(cin, cout, 2 * stride, stride=stride, padding=stride // 2 + stride % 2,
+                                output_padding=stride % 2)
+        inner = m
     x = torch.randn(2, cin, T, generator=g)
     act = SnakeBeta(cin, alpha_logscale=True)
     act.alpha.data = torch.randn(cin, generator=g) * 0.3
     act.beta.data = torch.randn(cin, generator=g) * 0.3
-    sd = {n: getattr(m, n).data.clone().double() for n in ("weight_g", "weight_v", "bias")}
+    pre = "conv." if causal else ""
+    sd = {pre + n: getattr(inner, n).data.clone().double() for n in ("weight_g", "weight_v", "bias")}
     want = oracle.wn_conv_transpose1d(sd, "", oracle.snake_beta(x, act.alpha.data, act.beta.data).double(),
-                                      stride=stride)
+                                      stride=stride, causal=causal)
     M.set_precision(precision)
     try:
-        got = m.to(DEV).forward_cl(ops.to_channels_last(x.to(DEV)), act=act.to(DEV)).permute(0, 2, 1)
+        m = m.to(DEV)
+        streamed = inner.stream_image(precision) is not None
+        got = m.forward_cl(ops.to_channels_last(x.to(DEV)), act=act.to(DEV)).permute(0, 2, 1)
+        M.CONVTR_STREAM[0] = False
+        per_phase = m.forward_cl(ops.to_channels_last(x.to(DEV)), act=act.to(DEV)).permute(0, 2, 1)
     finally:
+        M.CONVTR_STREAM[0] = True
         M.set_precision("fp32")
+    assert streamed == (cin % 16 == 0 and cin >= 32 and (stride * cout) % 64 == 0), streamed
+    assert got.shape == want.shape
     assert rel(got, want) <= tol
+    assert rel(got, per_phase) <= tol
 
 
 @pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
