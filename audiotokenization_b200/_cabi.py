@@ -47,6 +47,8 @@ _SIGNATURES = {
     "bc_lstm_tc_max_batch": (c_int, [c_int, c_int]),
     "bc_lstm_tc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "bc_lstm_tc_recurrent_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "bc_lstm_tc_recurrent_chunk_fwd": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
+    "bc_lstm_tc_ctas": (c_int, [c_int, c_int, c_int]),
     "bc_vq_encode": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "bc_vq_dequant": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
     "bc_fsq_encode": (c_int, [c_void_p] * 7 + [c_int] * 3 + [c_void_p]),

@@ -48,6 +48,9 @@ struct LstmTcParams {
   __nv_bfloat16* hx;       // [2][m_tiles][split][H/8][128][8]
   unsigned int* counters;  // [m_tiles][CNT_STRIDE]: one step counter per (batch tile, K chunk of h)
   int B, T, H, NS, nslot, n_slices, m_tiles;
+  int pre_rows, y_rows;    // rows (time steps) between consecutive batch items of pre / of y and skip (>= T: chunked sequences)
+  int t_base;              // global index of this launch's first step (exchange-buffer parity; > 0: continue from c_state / hx)
+  float* c_state;          // [m_tiles * 128][H] cell state carried between the chunks of a sequence (NULL: none)
   uint32_t idesc_wide, idesc_ns;   // N = split*NS (a_hi x [w_hi | w_lo]) and N = NS (a_lo x w_hi)
   long long* trace;   // debug: [step < 64][8] clock64 stamps of CTA (0,0), steps 100.. (NULL = off)
 };
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           // K chunk c of h_{t-1} is written by the KC/U n-slices that own its hidden units: each chunk is fetched as soon
           // as ITS producers have published (per-chunk step counters), so the copies and MMAs of the early chunks overlap
           // the stragglers of the later ones instead of waiting for the slowest of all n-slices
-          const __nv_bfloat16* src = p.hx + (size_t)((t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
+          const __nv_bfloat16* src = p.hx + (size_t)((p.t_base + t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
           for (int c = 0; c < nchunks; ++c, ++cc) {
             if (t > 0) {
               const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
@@ -217,13 +220,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
       const int m = (int)blockIdx.y + j * (int)gridDim.y;
       const int b = m * LM + row;
       row_ok[j] = j < ntile && b < p.B;
-      pre_row[j] = p.pre + (size_t)(row_ok[j] ? b : 0) * p.T * 4 * H + u_glb;
-      out_row[j] = (size_t)(row_ok[j] ? b : 0) * p.T * H + u_glb;
+      pre_row[j] = p.pre + (size_t)(row_ok[j] ? b : 0) * p.pre_rows * 4 * H + u_glb;
+      out_row[j] = (size_t)(row_ok[j] ? b : 0) * p.y_rows * H + u_glb;
       // exchange-buffer position of this thread's units: plane = u_glb / 8, element = u_glb % 8
       hx_off[j] = (size_t)(j < ntile ? m : 0) * hx_tile + ((size_t)(u_glb >> 3) * LM + row) * 8 + (u_glb & 7);
       counter[j] = p.counters + (j < ntile ? m : 0) * CNT_STRIDE + (n * U) / KC;
 #pragma unroll
-      for (int u = 0; u < UPW; ++u) c_state[j][u] = 0.f;
+      for (int u = 0; u < UPW; ++u)
+        c_state[j][u] = (p.c_state && p.t_base > 0 && row_ok[j]) ? p.c_state[(size_t)b * H + u_glb + u] : 0.f;
       // prefetch pre-activations of step 0
 #pragma unroll
       for (int g = 0; g < 4; ++g)
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
         // this batch tile waits for it.  The fences below wait for all earlier memory operations of the thread, so
         // nothing else (output store, skip load, next step's pre-activation loads) may be in flight before them.
         {
-          __nv_bfloat16* dst = p.hx + (size_t)(t & 1) * hx_parity + hx_off[j];
+          __nv_bfloat16* dst = p.hx + (size_t)((p.t_base + t) & 1) * hx_parity + hx_off[j];
           __nv_bfloat16 hi[UPW], lo[UPW];
 #pragma unroll
           for (int u = 0; u < UPW; ++u) {
@@ -332,6 +336,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
             __stcs(reinterpret_cast<float2*>(p.y + o), v);
           }
         }
+      }
+    }
+    if (p.c_state) {   // carry the cell state to the next chunk of the sequence
+#pragma unroll
+      for (int j = 0; j < TPC; ++j) {
+        if (!row_ok[j]) continue;
+        const int b = ((int)blockIdx.y + j * (int)gridDim.y) * LM + row;
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) p.c_state[(size_t)b * H + u_glb + u] = c_state[j][u];
       }
     }
   }
@@ -402,10 +415,12 @@ extern "C" int bc_lstm_tc_max_batch(int H, int precision) {
   return m_tiles * LM * (bc::policy().lstm_pingpong ? MAX_TPC : 1);
 }
 
-extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, const float* skip, float* y,
-                                        void* workspace, int B, int T, int H, int precision, bc_stream_t s) {
+static int lstm_tc_launch(const float* pre, const void* w_image, const float* skip, float* y, void* workspace,
+                          float* c_state, int B, int T, int pre_rows, int y_rows, int t_base, int H, int precision,
+                          bc_stream_t s) {
   BC_REQUIRE(pre && w_image && y && workspace, "lstm_tc: null pointer");
-  BC_REQUIRE(B > 0 && T > 0 && H > 0, "lstm_tc: bad shape B=%d T=%d H=%d", B, T, H);
+  BC_REQUIRE(B > 0 && T > 0 && H > 0 && pre_rows >= T && y_rows >= T && t_base >= 0, "lstm_tc: bad shape B=%d T=%d H=%d", B, T, H);
+  BC_REQUIRE(t_base == 0 || c_state, "lstm_tc: continuing a sequence needs the carried cell state");
   LstmTcPlan pl;
   if (!lstm_tc_plan(B, H, precision, &pl))
     return bc::fail(BC_EUNSUPPORTED, "lstm_tc: H=%d precision=%d has no tensor-core plan", H, precision);
@@ -423,11 +438,16 @@ extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, c
   p.trace = g_lstm_trace;
   p.pre = pre; p.wimg = reinterpret_cast<const uint4*>(w_image); p.skip = skip; p.y = y;
   p.hx = reinterpret_cast<__nv_bfloat16*>(workspace);
-  p.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + ((pl.hx_bytes + 127) & ~size_t(127)));
+  const size_t hx_pad = (pl.hx_bytes + 127) & ~size_t(127);
+  p.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + hx_pad);
   p.B = B; p.T = T; p.H = H; p.NS = pl.NS; p.nslot = pl.nslot; p.n_slices = pl.n_slices; p.m_tiles = pl.m_tiles;
+  p.pre_rows = pre_rows; p.y_rows = y_rows; p.t_base = t_base; p.c_state = c_state;
   p.idesc_wide = bc::tc::idesc_bf16_m128(pl.split * pl.NS);
   p.idesc_ns = bc::tc::idesc_bf16_m128(pl.NS);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, pl.ws_bytes, st);
+  // a new sequence starts from h = 0 (the exchange buffer) and fresh step counters; a continued one keeps h and only
+  // restarts the counters (they count the steps of THIS launch)
+  cudaError_t e = t_base == 0 ? cudaMemsetAsync(workspace, 0, pl.ws_bytes, st)
+                              : cudaMemsetAsync(reinterpret_cast<uint8_t*>(workspace) + hx_pad, 0, pl.ws_bytes - hx_pad, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaMemsetAsync(lstm_tc)");
   void* kern = nullptr;
   if (pl.split == 2) kern = pl.tpc == 2 ? (void*)lstm_tc_kernel<2, 2, 2> : (void*)lstm_tc_kernel<2, 2, 1>;
@@ -438,6 +458,24 @@ extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, c
   e = cudaLaunchCooperativeKernel(kern, dim3(pl.n_slices, pl.grid_y), dim3(L_THREADS), args, pl.smem, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaLaunchCooperativeKernel(lstm_tc)");
   return BC_OK;
+}
+
+extern "C" int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, const float* skip, float* y,
+                                        void* workspace, int B, int T, int H, int precision, bc_stream_t s) {
+  return lstm_tc_launch(pre, w_image, skip, y, workspace, nullptr, B, T, T, T, 0, H, precision, s);
+}
+
+extern "C" int bc_lstm_tc_recurrent_chunk_fwd(const float* pre, const void* w_image, const float* skip, float* y,
+                                              void* workspace, float* c_state, int B, int T_chunk, int pre_rows, int y_rows,
+                                              int t_base, int H, int precision, bc_stream_t s) {
+  BC_REQUIRE(c_state, "lstm_tc(chunk): null cell-state buffer");
+  return lstm_tc_launch(pre, w_image, skip, y, workspace, c_state, B, T_chunk, pre_rows, y_rows, t_base, H, precision, s);
+}
+
+extern "C" int bc_lstm_tc_ctas(int B, int H, int precision) {
+  LstmTcPlan pl;
+  if (B <= 0 || !lstm_tc_plan(B, H, precision, &pl)) return 0;
+  return pl.n_slices * pl.grid_y;
 }
 
 // debug hook (not part of the product path): device buffer of 64*8 int64 receiving clock64 stamps of CTA (0,0)

@@ -441,6 +441,37 @@ def lstm_recurrent_tc(pre: torch.Tensor, w_image: torch.Tensor, skip: Optional[t
     return y
 
 
+def lstm_tc_ctas(B: int, H: int, precision: str) -> int:
+    """CTAs one tensor-core LSTM launch of batch ``B`` occupies (0: no plan)."""
+    if precision == "fp32":
+        return 0
+    return int(load_library().bc_lstm_tc_ctas(B, H, PRECISIONS[precision]))
+
+
+def lstm_tc_workspace(B: int, H: int, precision: str, device) -> torch.Tensor:
+    return torch.empty(load_library().bc_lstm_tc_workspace_bytes(B, H, PRECISIONS[precision]), device=device, dtype=torch.uint8)
+
+
+def lstm_recurrent_tc_chunk(pre: torch.Tensor, w_image: torch.Tensor, skip: Optional[torch.Tensor], y: torch.Tensor,
+                            ws: torch.Tensor, c_state: torch.Tensor, t_base: int, precision: str) -> None:
+    """One chunk of a chunked sequence (bc_lstm_tc_recurrent_chunk_fwd).  ``pre`` [B,Tc,4H], ``y`` / ``skip`` [B,Tc,H] may be
+    time slices of larger tensors (batch stride = the full length); the innermost two dimensions must be dense."""
+    B, Tc, H4 = pre.shape
+    H = H4 // 4
+    for t, inner in ((pre, H4), (y, H)) + (((skip, H),) if skip is not None else ()):
+        if t.stride(2) != 1 or t.stride(1) != inner or (B > 1 and t.stride(0) % inner != 0):
+            raise ValueError("lstm_recurrent_tc_chunk: tensors must be time slices of dense [B,T,C] tensors")
+    if skip is not None and (skip.stride(0) != y.stride(0) and B > 1):
+        raise ValueError("lstm_recurrent_tc_chunk: skip and y must share their batch stride")
+    pre_rows = pre.stride(0) // H4 if B > 1 else Tc
+    y_rows = y.stride(0) // H if B > 1 else Tc
+    with _Timed(("lstm", H, H, 0, 0, 0, Tc, B, precision), 2.0 * B * Tc * 4 * H * H, pre.device, "lstm_tc_kernel"):
+        check(load_library().bc_lstm_tc_recurrent_chunk_fwd(ptr(pre), ptr(w_image), ptr(skip), ptr(y), ptr(ws), ptr(c_state),
+                                                            B, Tc, pre_rows, y_rows, int(t_base), H, PRECISIONS[precision],
+                                                            stream_ptr(pre.device)), "bc_lstm_tc_recurrent_chunk_fwd")
+    _count()
+
+
 def vq_encode(z: torch.Tensor, w_in: Optional[torch.Tensor], b_in: Optional[torch.Tensor], cb_norm: torch.Tensor,
               want_margin: bool = False, want_ze: bool = False):
     """z [N,C] -> (idx int32 [N], margin [N] | None, z_e [N,D] | None)."""

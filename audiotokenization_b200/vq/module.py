@@ -23,6 +23,17 @@ from .alias_free_torch import Activation1d
 
 _PRECISION = ["fp32"]
 LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
+LSTM_WAVEFRONT = [True]     # ... and, for batches whose two layers fit the chip side by side, as a two-layer wave front
+LSTM_WAVEFRONT_CHUNK = [128]   # steps per chunk of the wave front
+
+
+def _cabi_sm_count() -> int:
+    from .. import _cabi
+    c = _cabi.__dict__.setdefault("_SM_COUNT", {})
+    dev = torch.cuda.current_device()
+    if dev not in c:
+        c[dev] = _cabi.device_info(dev)["sm_count"]
+    return c[dev]
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
 CONVTR_STREAM = [True]  # ... and transposed convs as ONE launch of it (all phases as channel blocks)
@@ -555,20 +566,74 @@ class ResLSTM(nn.Module):
         self.skip = skip
         self.lstm = _LSTMParams(dimension, dimension, num_layers)
 
+    def _input_proj(self, h, l, precision):
+        """W_ih h + b_ih + b_hh for every step: one dense K = 1 contraction."""
+        H = self.lstm.hidden_size
+        nt = _stream_tile(h.shape[2], 4 * H, 1, 1, 1, precision)
+        if nt is not None:
+            return ops.conv1d_stream(h, self.lstm.input_proj_stream(l, precision, nt), self.lstm.packed(l)[1], k=1,
+                                     c_out=4 * H, t_out=h.shape[1], precision=precision)
+        w_in, bias, prec = self.lstm.input_proj_for(l, precision)
+        return ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
+
+    def _wavefront_chunk(self, B, T, precision):
+        """Chunk length of the two-layer wave front, or 0 when it does not apply: two layers, a tensor-core plan, and both
+        layers' launches co-resident (twice the CTAs of one launch fit the SMs: batches up to 128 in split precision)."""
+        if not LSTM_WAVEFRONT[0] or self.lstm.num_layers != 2 or precision == "fp32" or not LSTM_TENSOR_CORE[0]:
+            return 0
+        H = self.lstm.hidden_size
+        ctas = ops.lstm_tc_ctas(B, H, precision)
+        if ctas == 0 or 2 * ctas > _cabi_sm_count():
+            return 0
+        chunk = LSTM_WAVEFRONT_CHUNK[0]
+        return chunk if T >= 3 * chunk else 0
+
+    def _forward_wavefront(self, x_cl, precision, chunk):
+        """Layer 1 runs on chunk c (input projection of layer 0's output + recurrence, side stream) while layer 0 runs on
+        chunk c + 1 (current stream): T + chunk sequential steps instead of 2 T.  Same kernels, same arithmetic and same
+        order of operations per element as the layer-by-layer schedule, so the results are bit-identical."""
+        B, T, C = x_cl.shape
+        H = self.lstm.hidden_size
+        dev = x_cl.device
+        main = torch.cuda.current_stream(dev)
+        side = self.__dict__.setdefault("_side_stream", {}).setdefault(dev, torch.cuda.Stream(device=dev))
+        pre0 = self._input_proj(x_cl, 0, precision)                                    # [B, T, 4H]
+        img0, img1 = self.lstm.recurrent_image_for(0, precision), self.lstm.recurrent_image_for(1, precision)
+        ws0, ws1 = ops.lstm_tc_workspace(B, H, precision, dev), ops.lstm_tc_workspace(B, H, precision, dev)
+        rows = (B + 127) // 128 * 128
+        c0, c1 = torch.empty((rows, H), device=dev), torch.empty((rows, H), device=dev)
+        n_chunks = (T + chunk - 1) // chunk
+        h0 = torch.empty((n_chunks, B, chunk, H), device=dev)                           # layer 0's output, chunk-major (dense per chunk)
+        y = torch.empty((B, T, H), device=dev)
+        done0 = [torch.cuda.Event() for _ in range(n_chunks)]
+        for c in range(n_chunks):
+            t0, t1 = c * chunk, min(T, (c + 1) * chunk)
+            ops.lstm_recurrent_tc_chunk(pre0[:, t0:t1], img0, None, h0[c][:, : t1 - t0], ws0, c0, t0, precision)
+            done0[c].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done0[c])
+                hc = h0[c][:, : t1 - t0]
+                pre1 = self._input_proj(hc if t1 - t0 == chunk else hc.contiguous(), 1, precision)
+                ops.lstm_recurrent_tc_chunk(pre1, img1, x_cl[:, t0:t1] if self.skip else None, y[:, t0:t1], ws1, c1, t0, precision)
+        fin = torch.cuda.Event()
+        fin.record(side)
+        main.wait_event(fin)
+        for t in (pre0, h0, ws0, ws1, c0, c1, y, x_cl):
+            t.record_stream(side)
+        return y
+
     def forward_cl(self, x_cl):
         h = x_cl
         n = self.lstm.num_layers
         precision = get_precision()
         H = self.lstm.hidden_size
         tc_batch = ops.lstm_tc_max_batch(H, precision) if LSTM_TENSOR_CORE[0] else 0
+        if tc_batch > 0:
+            chunk = self._wavefront_chunk(x_cl.shape[0], x_cl.shape[1], precision)
+            if chunk:
+                return self._forward_wavefront(x_cl, precision, chunk)
         for l in range(n):
-            nt = _stream_tile(h.shape[2], 4 * H, 1, 1, 1, precision)
-            if nt is not None:
-                pre = ops.conv1d_stream(h, self.lstm.input_proj_stream(l, precision, nt), self.lstm.packed(l)[1], k=1,
-                                        c_out=4 * H, t_out=h.shape[1], precision=precision)
-            else:
-                w_in, bias, prec = self.lstm.input_proj_for(l, precision)
-                pre = ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
+            pre = self._input_proj(h, l, precision)
             skip = x_cl if (self.skip and l == n - 1) else None
             if tc_batch > 0:
                 h = ops.lstm_recurrent_tc(pre, self.lstm.recurrent_image_for(l, precision), skip, precision, tc_batch)

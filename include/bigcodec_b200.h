@@ -205,6 +205,17 @@ int bc_lstm_tc_max_batch(int H, int precision);
 size_t bc_lstm_tc_workspace_bytes(int B, int H, int precision);
 int bc_lstm_tc_recurrent_fwd(const float* pre, const void* w_image, const float* skip, float* y,
                              void* workspace, int B, int T, int H, int precision, bc_stream_t s);
+/* The same recurrence over ONE CHUNK of a longer sequence: steps [t_base, t_base + T_chunk).  pre / y / skip point at the
+ * chunk's first step; consecutive batch items are pre_rows (resp. y_rows) steps apart.  The hidden state travels in the
+ * workspace (same workspace for every chunk of a sequence, chunks in order on one stream), the cell state in
+ * c_state [ceil(B/128)*128][H] floats (written by every chunk, read when t_base > 0).  With this the two layers of a ResLSTM
+ * run as a wave front on two streams -- layer 1 on chunk c while layer 0 is on chunk c+1 -- which halves the number of
+ * sequential steps of a small batch (host side: vq/module.py ResLSTM).  bc_lstm_tc_ctas = CTAs one launch occupies
+ * (two launches are co-resident when twice that fits the SM count). */
+int bc_lstm_tc_recurrent_chunk_fwd(const float* pre, const void* w_image, const float* skip, float* y,
+                                   void* workspace, float* c_state, int B, int T_chunk, int pre_rows, int y_rows,
+                                   int t_base, int H, int precision, bc_stream_t s);
+int bc_lstm_tc_ctas(int B, int H, int precision);
 
 /* ---- factorized VQ -------------------------------------------------------- */
 /* Replaces FactorizedVectorQuantize.forward / decode_latents in eval mode

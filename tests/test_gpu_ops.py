@@ -497,6 +497,33 @@ def test_res_lstm_tensor_core_recurrence(precision, tol, H, layers, B, T):
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("H,B,T", [(512, 64, 800), (512, 1, 1000), (256, 100, 500), (128, 3, 384), (512, 128, 390)])
+def test_res_lstm_two_layer_wave_front_is_bit_identical(precision, H, B, T):
+    """Small batches: layer 1 runs one chunk behind layer 0 on a second stream (chunked launches with the hidden state in
+    the workspace and the cell state carried in a buffer).  Same kernels and the same per-element arithmetic as the
+    layer-by-layer schedule: results must be bit-identical, partial last chunks included."""
+    g = gen(H + B + T)
+    m = M.ResLSTM(H, num_layers=2).to(DEV)
+    x = torch.randn(B, H, T, generator=g).to(DEV)
+    M.set_precision(precision)
+    try:
+        assert m._wavefront_chunk(B, T, precision) == 128
+        got = m(x)
+        again = m(x)
+        M.LSTM_WAVEFRONT[0] = False
+        ref = m(x)
+    finally:
+        M.LSTM_WAVEFRONT[0] = True
+        M.set_precision("fp32")
+    assert torch.equal(got, again)
+    assert torch.equal(got, ref)
+    sd = {"lstm." + k: v.data.clone().cpu() for k, v in m.lstm.named_parameters()}
+    if B * T <= 60000:
+        want = oracle.res_lstm(sd, "", x.cpu(), 2)
+        assert rel(got, want) <= (1e-4 if precision == "bf16x3" else 3e-2)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_res_lstm_tensor_core_gates_saturate_instead_of_overflowing(precision):
     """the cell state is unbounded (|c| grows by up to 1 per step when i, f saturate), and a
     (1 - e) / (1 + e) tanh with e = exp(-2x) turns into 0 or NaN for x < -44.  Drive |c| and the g gate far past
