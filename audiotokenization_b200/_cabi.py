@@ -37,6 +37,10 @@ _SIGNATURES = {
     "bc_stream_plan": (c_int, [c_int] * 7 + [POINTER(c_int)]),
     "bc_conv1d_stream_fwd": (c_int, [c_void_p] * 7 + [c_int] * 11 + [c_void_p]),
     "bc_resunit_stream_fwd": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_void_p]),
+    "bc_stream_pair_ok": (c_int, [c_int] * 7),
+    "bc_conv1d_stream_pair_fwd": (c_int, [c_void_p] * 7 + [c_int] * 11 + [c_void_p]),
+    "bc_resunit_stream_pair_fwd": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_void_p]),
+    "bc_convtr1d_stream_pair_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bc_convtr1d_stream_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bc_convtr1d_fwd": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
     "bc_lstm_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -95,7 +95,7 @@ constexpr int MAX_TPU = 8;             // taps per weight unit (issue block is u
 constexpr uint32_t UNIT_MAX_BYTES = 32768;
 
 enum { B_A_FULL = 0, B_A_EMPTY = 4, B_B_FULL = 8, B_B_EMPTY = 16, B_ACC1_FULL = 24, B_ACC1_EMPTY = 26,
-       B_A2_FULL = 28, B_A2_EMPTY = 30, B_ACC2_FULL = 32, B_ACC2_EMPTY = 34, N_BARS = 36 };
+       B_A2_FULL = 28, B_A2_EMPTY = 30, B_ACC2_FULL = 32, B_ACC2_EMPTY = 34, B_B_READY = 36, N_BARS = 44 };
 
 struct SParams {
   const float* x;
@@ -115,6 +115,7 @@ struct SParams {
   int slab_rows, rpp, NA, NB, acc_stages, acc_stride, epi_warps;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
   int tiles_per_item, tiles_per_nt, total_tiles;
+  int pairs_per_nt, total_pairs;   // pair form: tile pairs (2q, 2q+1) inside one n-tile; an odd count leaves rank 1 a phantom tile
   uint32_t idesc;
   int tmem_cols;
   long long* trace;   // debug: [tile_it < 64][16] clock64 stamps / wait totals of CTA 0 (NULL = off)
@@ -169,6 +170,33 @@ struct TilePos {
   }
 };
 
+// The tiles one CTA walks, in order.  Single-CTA form: tiles first, first + step, ... (TilePos, no division per tile).
+// Pair form: the cluster takes the tile PAIRS pi, pi + npairs, ...; pair Q covers tiles 2q + {0, 1} of n-tile nt = Q / ppn
+// and this CTA the one of its rank (`valid` false: the phantom tile behind an odd count -- staged as zeros, never stored).
+template <bool PAIR>
+struct Walk {
+  int nt, b, tt;
+  bool valid;
+  TilePos tp;
+  int Q;
+  __device__ __forceinline__ void locate(const SParams& p, int rank) {
+    nt = Q / p.pairs_per_nt;
+    const int ti = 2 * (Q - nt * p.pairs_per_nt) + rank;
+    valid = ti < p.tiles_per_nt;
+    const int tl = valid ? ti : p.tiles_per_nt - 1;
+    b = tl / p.tiles_per_item;
+    tt = tl - b * p.tiles_per_item;
+  }
+  __device__ __forceinline__ void init(const SParams& p, int first, int rank) {
+    if (PAIR) { Q = first; locate(p, rank); }
+    else { tp.init(first, p.tiles_per_item, p.B); nt = tp.nt; b = tp.b; tt = tp.tt; valid = true; }
+  }
+  __device__ __forceinline__ void advance(const SParams& p, int step, int rank) {
+    if (PAIR) { Q += step; locate(p, rank); }
+    else { tp.advance(step, p.tiles_per_item, p.B); nt = tp.nt; b = tp.b; tt = tp.tt; }
+  }
+};
+
 // stage stamps are compiled in only with -DBC_TRACE (BC_TRACE=1 python -m audiotokenization_b200.build)
 #ifdef BC_TRACE
 #define STRACE(ev) do { if (p.trace && blockIdx.x == 0 && it < 64 && lane == 0) p.trace[it * 16 + (ev)] = clock64(); } while (0)
@@ -178,10 +206,16 @@ struct TilePos {
 #define STRACE_ON false
 #endif
 
-template <int SPLIT, bool FUSE>
-__global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(const SParams p) {
+template <int SPLIT, bool FUSE, bool PAIR>
+__device__ __forceinline__ void conv_stream_body(const SParams& p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = PAIR ? (int)cluster_rank() : 0;
+  // hand-offs towards the MMA thread come from both CTAs of a pair and land on the leader's barrier; hand-offs from it
+  // are multicast commits that every CTA waits for on its local copy
+#define ARRIVE_MMA(bar) do { if (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar); } while (0)
+#define WAIT_MMA(bar, par) do { if (PAIR) mbar_wait_cluster(bar, par); else mbar_wait(bar, par); } while (0)
+#define COMMIT(bar) do { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); } while (0)
   using R = Roles<FUSE>;
   constexpr int N_PROD = R::PROD, MID_WARP0 = R::MID0, EPI_WARP0 = R::EPI0, LOAD_WARP = R::LOAD, MMA_WARP = R::MMA;
   constexpr int S_THREADS = R::THREADS, P_BATCH = R::PB;
@@ -201,21 +235,23 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
 
   if (tid == 0) {
+    constexpr int NCTA = PAIR ? 2 : 1;
     for (int s = 0; s < 4; ++s) {
-      mbar_init(BAR(B_A_FULL + s), N_PROD / p.NA);
+      mbar_init(BAR(B_A_FULL + s), NCTA * (N_PROD / p.NA));
       mbar_init(BAR(B_A_EMPTY + s), 1);
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(BAR(B_B_FULL + s), 1);
       mbar_init(BAR(B_B_EMPTY + s), 1);
+      mbar_init(BAR(B_B_READY + s), 2);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_ACC1_FULL + s), 1);
-      mbar_init(BAR(B_ACC1_EMPTY + s), FUSE ? MID_WARPS : p.epi_warps);
-      mbar_init(BAR(B_A2_FULL + s), MID_WARPS);
+      mbar_init(BAR(B_ACC1_EMPTY + s), NCTA * (FUSE ? MID_WARPS : p.epi_warps));
+      mbar_init(BAR(B_A2_FULL + s), NCTA * MID_WARPS);
       mbar_init(BAR(B_A2_EMPTY + s), 1);
       mbar_init(BAR(B_ACC2_FULL + s), 1);
-      mbar_init(BAR(B_ACC2_EMPTY + s), p.epi_warps);
+      mbar_init(BAR(B_ACC2_EMPTY + s), NCTA * p.epi_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -233,17 +269,25 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     }
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                     // both CTAs: barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int first = blockIdx.x, step = gridDim.x;
+  // single CTA: tiles blockIdx.x, + gridDim.x, ...; pair: the cluster's tile pairs (blockIdx.x / 2), + gridDim.x / 2, ...
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_units = PAIR ? p.total_pairs : p.total_tiles;
   const bool defer = FUSE && p.acc_stages == 2;   // 1x1 conv of tile i issued after the K-tap conv of tile i+1
   int n_my = 0;
-  for (int tile = first; tile < p.total_tiles; tile += step) ++n_my;
+  for (int tile = first; tile < n_units; tile += step) ++n_my;
 
   const bool freerun = DBG_SKIP(8);      // timing experiment: MMA thread free-runs on whatever is in smem
   const bool free_b = DBG_SKIP(16);      // ... only the weight ring is ignored
@@ -266,14 +310,14 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     const int ph_first = r_first % p.stride, rr_first = r_first / p.stride;   // once per thread
     const int rr_step = rstep / p.stride, ph_step = rstep - rr_step * p.stride;
     const uint32_t dst_off = (uint32_t)(c4 >> 1) * plane_bytes + (uint32_t)(c4 & 1) * 8u;
-    int it = 0;
     int slot_c = 0, use_c = 0, sq = 0;   // running ring position over ALL stages (every team counts every stage)
-    TilePos tp;
-    tp.init(first, p.tiles_per_item, p.B);
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it, tp.advance(step, p.tiles_per_item, p.B)) {
+    Walk<PAIR> tp;
+    tp.init(p, first, rank);
+    for (int it = 0; it < n_my; ++it, tp.advance(p, step, rank)) {
       const int b = tp.b;
       const int t0 = tp.tt * BM;
-      const int g0row = t0 * p.stride - p.pad_left + (tp.nt >= p.nt_shift ? 1 : 0);
+      // a phantom tile (pair form, odd tile count) is staged as if it lay entirely beyond the item: all zeros
+      const int g0row = tp.valid ? t0 * p.stride - p.pad_left + (tp.nt >= p.nt_shift ? 1 : 0) : p.T_in + p.slab_rows;
       const float* xb = p.x + (size_t)b * p.T_in * p.C_in + c4 * 4;
       long long wE = 0;
       for (int g = 0; g < p.groups; ++g, ++sq) {
@@ -354,7 +398,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         if (!waited) mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(B_A_FULL + slot));
+        if (lane == 0) ARRIVE_MMA(BAR(B_A_FULL + slot));
         if (g == p.groups - 1 && tw == 0) STRACE(1);
       }
       if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) p.trace[it * 16 + 12] = wE;
@@ -365,16 +409,20 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     // ======================= WEIGHTS: unit ring, same order as the MMA warp consumes =======================
     if (lane == 0 && !freerun && !free_b) {
       uint32_t slot = 0, phase = 1;   // ring position; `phase` = parity a free slot's empty barrier must have completed
-      TilePos ltp;
-      ltp.init(first, p.tiles_per_item, p.B);
+      Walk<PAIR> ltp;
+      ltp.init(p, first, rank);
       const uint32_t uB = smem_u32(sB);
       const int nchunk = p.N / A2_CH;
       const int last = defer ? n_my : n_my - 1;
+      // pair form: the image holds, per n-tile, rank 0's half of every unit (rows [0, N/2) of each k-plane) and then
+      // rank 1's; p.tap_bytes is already the per-rank size
+      const size_t nt_bytes = (size_t)p.groups * p.K * p.tap_bytes;
+      const uint8_t* w1r = PAIR ? p.w1 + (size_t)rank * (p.N / 16) * p.tap_bytes : p.w1;
       for (int it = 0; it <= last; ++it) {
         if (it < n_my) {
           const int nt = ltp.nt;
-          ltp.advance(step, p.tiles_per_item, p.B);
-          const uint8_t* wnt = p.w7 + (size_t)nt * p.groups * p.K * p.tap_bytes;
+          ltp.advance(p, step, rank);
+          const uint8_t* wnt = p.w7 + (PAIR ? (size_t)(2 * nt + rank) : (size_t)nt) * nt_bytes;
           for (int g = 0; g < p.groups; ++g)
             for (int u = 0; u < p.upg; ++u) {
               const int k0 = u * p.tpu, k1 = min(p.K, k0 + p.tpu);
@@ -390,7 +438,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
             for (int c = 0; c < nchunk; ++c)
               for (int gu = 0; gu < 4 / p.gpu1; ++gu) {
                 mbar_wait(BAR(B_B_EMPTY + slot), phase);
-                bulk_g2s(uB + slot * p.unit_bytes, p.w1 + (size_t)(c * 4 + gu * p.gpu1) * p.tap_bytes, ((uint32_t)p.gpu1 * p.tap_bytes) >> DBG_BSHIFT,
+                bulk_g2s(uB + slot * p.unit_bytes, w1r + (size_t)(c * 4 + gu * p.gpu1) * p.tap_bytes, ((uint32_t)p.gpu1 * p.tap_bytes) >> DBG_BSHIFT,
                          BAR(B_B_FULL + slot));
                 if (++slot == (uint32_t)p.NB) { slot = 0; phase ^= 1u; }
               }
@@ -398,7 +446,20 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         }
       }
     }
-   } else if (warp == MMA_WARP) {
+   } else if (PAIR && warp == LOAD_WARP + 2) {
+    // ======================= RELAY (pair form): this CTA's half of a weight unit has landed -> tell the leader =======================
+    // A bulk copy completes on a barrier of its own CTA; the leader's MMA thread waits on B_READY (one arrival per CTA).
+    if (lane == 0 && !freerun && !free_b) {
+      const int nchunk = p.N / A2_CH;
+      long long units = (long long)n_my * p.groups * p.upg + (FUSE ? (long long)n_my * nchunk * (4 / p.gpu1) : 0);
+      uint32_t slot = 0, phase = 0;
+      for (; units > 0; --units) {
+        mbar_wait(BAR(B_B_FULL + slot), phase);
+        mbar_arrive_leader(BAR(B_B_READY + slot));
+        if (++slot == (uint32_t)p.NB) { slot = 0; phase ^= 1u; }
+      }
+    }
+   } else if (warp == MMA_WARP && (!PAIR || rank == 0)) {
     // ======================= MMA issue: one elected lane runs the whole role =======================
     // The tensor pipe queues only a couple of MMAs, so every instruction between two MMA bursts costs tensor time
     // (scripts/probes/mma_probe.cu, modes 100+: a satisfied mbarrier try_wait ~55 cycles, a tcgen05.commit ~35-60,
@@ -408,8 +469,9 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     // behind the first tap of the current one (BC_STREAM_DEFER_COMMITS / BC_STREAM_PREFETCH_WAITS).
     const uint32_t hi_d = desc_hi(128u);
     const uint32_t uA = smem_u32(sA), uB = smem_u32(sB), uA2 = smem_u32(sA2);
-    const uint32_t b_kplane = (uint32_t)p.N * 16u;       // LBO of the B operand: stride between the two k-planes
-    const uint32_t b_lo_off = ((uint32_t)p.N * 32u) >> 4;  // lo split of a tap, in 16-byte units
+    const uint32_t n_rows = PAIR ? (uint32_t)p.N / 2u : (uint32_t)p.N;   // B rows held by this SM
+    const uint32_t b_kplane = n_rows * 16u;              // LBO of the B operand: stride between the two k-planes
+    const uint32_t b_lo_off = (n_rows * 32u) >> 4;       // lo split of a tap, in 16-byte units
     const uint32_t tap16 = p.tap_bytes >> 4;
     const uint32_t a_sp = a_split >> 4;
     const int nchunk = p.N / A2_CH;
@@ -424,26 +486,29 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       uint32_t pend_b = 0, pend_a = 0, pend_acc = 0;     // commits owed for the previous unit (barrier addresses, 0 = none)
       bool a_ready = false, b_ready = false;              // the next slab / weight unit has already been waited for
       long long units_left = (long long)n_my * p.groups * p.upg + (FUSE ? (long long)n_my * nchunk * units2 : 0);
-#define FLUSH_COMMITS() do { if (pend_b) umma_commit(pend_b); if (pend_a) umma_commit(pend_a); if (pend_acc) umma_commit(pend_acc); \
+#define FLUSH_COMMITS() do { if (pend_b) COMMIT(pend_b); if (pend_a) COMMIT(pend_a); if (pend_acc) COMMIT(pend_acc); \
                              pend_b = pend_a = pend_acc = 0; } while (0)
+#define MMA_RT(d_, a_, b_, acc_) do { if (PAIR) mma2_bf16_rt(d_, a_, b_, hi_d, hi_d, idesc, acc_); else mma_bf16_raw_rt(d_, a_, b_, hi_d, hi_d, idesc, acc_); } while (0)
+#define MMA_ACC(d_, a_, b_) do { if (PAIR) mma2_bf16_raw<true>(d_, a_, b_, hi_d, hi_d, idesc); else mma_bf16_raw<true>(d_, a_, b_, hi_d, hi_d, idesc); } while (0)
+#define B_RDY (PAIR ? B_B_READY : B_B_FULL)
 #define PREFETCH_B() do { if (BC_STREAM_PREFETCH_WAITS && --units_left > 0 && !freerun && !free_b) { \
                             uint32_t nb = bslot + 1, nph = bph; if (nb == (uint32_t)p.NB) { nb = 0; nph ^= 1u; } \
-                            mbar_wait(BAR(B_B_FULL + nb), nph); b_ready = true; } } while (0)
+                            WAIT_MMA(BAR(B_RDY + nb), nph); b_ready = true; } } while (0)
       for (int it = 0; it <= last; ++it) {
         if (it < n_my) {
           const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
           FLUSH_COMMITS();
-          mbar_wait(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
+          WAIT_MMA(BAR(B_ACC1_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(as * p.acc_stride);
           STRACE(2);
           for (int g = 0; g < p.groups; ++g) {
-            if (!a_ready && !freerun) mbar_wait(BAR(B_A_FULL + aslot), aph);
+            if (!a_ready && !freerun) WAIT_MMA(BAR(B_A_FULL + aslot), aph);
             a_ready = false;
             const uint32_t a_lo0 = desc_lo(uA + aslot * p.a_stage, plane_bytes);
             int k = 0;
             for (int u = 0; u < p.upg; ++u) {
-              if (!b_ready && !freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
+              if (!b_ready && !freerun && !free_b) WAIT_MMA(BAR(B_RDY + bslot), bph);
               b_ready = false;
               const int nt = min(p.tpu, p.K - k);
               uint32_t off[MAX_TPU];
@@ -456,11 +521,11 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
               for (int j = 0; j < MAX_TPU; ++j) {
                 if (j < nt) {
                   const uint32_t a_lo = a_lo0 + off[j], b_lo = b_lo0 + (uint32_t)j * tap16;
-                  if (j == 0) mma_bf16_raw_rt(d, a_lo, b_lo, hi_d, hi_d, idesc, (g | k) ? 1u : 0u);
-                  else        mma_bf16_raw<true>(d, a_lo, b_lo, hi_d, hi_d, idesc);
+                  if (j == 0) MMA_RT(d, a_lo, b_lo, (g | k) ? 1u : 0u);
+                  else        MMA_ACC(d, a_lo, b_lo);
                   if (SPLIT == 2) {
-                    mma_bf16_raw<true>(d, a_lo, b_lo + b_lo_off, hi_d, hi_d, idesc);   // a_hi * w_lo
-                    mma_bf16_raw<true>(d, a_lo + a_sp, b_lo, hi_d, hi_d, idesc);       // a_lo * w_hi
+                    MMA_ACC(d, a_lo, b_lo + b_lo_off);   // a_hi * w_lo
+                    MMA_ACC(d, a_lo + a_sp, b_lo);       // a_lo * w_hi
                   }
                 }
                 if (j == 0) {   // housekeeping behind the first tap
@@ -469,7 +534,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
                   if (BC_STREAM_PREFETCH_WAITS && last_u && g + 1 < p.groups && !freerun) {
                     uint32_t na = aslot + 1, nph = aph;
                     if (na == (uint32_t)p.NA) { na = 0; nph ^= 1u; }
-                    mbar_wait(BAR(B_A_FULL + na), nph);
+                    WAIT_MMA(BAR(B_A_FULL + na), nph);
                     a_ready = true;
                   }
                 }
@@ -492,18 +557,18 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
           if (j >= 0 && j < n_my) {
             const int as = p.acc_stages == 2 ? (j & 1) : 0, ause = p.acc_stages == 2 ? (j >> 1) : j;
             FLUSH_COMMITS();            // MID(j) may be waiting for the accumulator commit that is still owed
-            mbar_wait(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
+            WAIT_MMA(BAR(B_ACC2_EMPTY + as), (uint32_t)((ause & 1) ^ 1));
             tc_fence_after();
             { const int it = j; STRACE(6); }
             const uint32_t d2 = tmem_base + (uint32_t)(as * p.acc_stride + p.N);
             for (int c = 0; c < nchunk; ++c, ++a2seq) {
               const uint32_t s2 = a2seq & 1u, u2 = a2seq >> 1;
               FLUSH_COMMITS();
-              mbar_wait(BAR(B_A2_FULL + s2), u2 & 1u);
+              WAIT_MMA(BAR(B_A2_FULL + s2), u2 & 1u);
               tc_fence_after();
               const uint32_t a_lo0 = desc_lo(uA2 + s2 * a2_chunk, A2_PLANE);
               for (uint32_t gu = 0; gu < units2; ++gu) {
-                if (!b_ready && !freerun && !free_b) mbar_wait(BAR(B_B_FULL + bslot), bph);
+                if (!b_ready && !freerun && !free_b) WAIT_MMA(BAR(B_RDY + bslot), bph);
                 b_ready = false;
                 const uint32_t b_lo0 = desc_lo(uB + bslot * p.unit_bytes, b_kplane);
                 const uint32_t gc0 = gu * (uint32_t)p.gpu1;
@@ -512,10 +577,10 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
                   if (gg < p.gpu1) {
                     const uint32_t gc = gc0 + (uint32_t)gg;
                     const uint32_t a_lo = a_lo0 + gc * ((2u * A2_PLANE) >> 4), b_lo = b_lo0 + (uint32_t)gg * tap16;
-                    mma_bf16_raw_rt(d2, a_lo, b_lo, hi_d, hi_d, idesc, ((uint32_t)c | gc) ? 1u : 0u);
+                    MMA_RT(d2, a_lo, b_lo, ((uint32_t)c | gc) ? 1u : 0u);
                     if (SPLIT == 2) {
-                      mma_bf16_raw<true>(d2, a_lo, b_lo + b_lo_off, hi_d, hi_d, idesc);
-                      mma_bf16_raw<true>(d2, a_lo + (a2_split >> 4), b_lo, hi_d, hi_d, idesc);
+                      MMA_ACC(d2, a_lo, b_lo + b_lo_off);
+                      MMA_ACC(d2, a_lo + (a2_split >> 4), b_lo);
                     }
                   }
                   if (gg == 0) {
@@ -539,6 +604,9 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       FLUSH_COMMITS();
 #undef FLUSH_COMMITS
 #undef PREFETCH_B
+#undef MMA_RT
+#undef MMA_ACC
+#undef B_RDY
     }
     __syncwarp();
    }
@@ -569,7 +637,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
             if (c == nchunk - 1 && hh == MID_HALVES - 1) {   // this warp's share of acc1 is in registers: hand the accumulator back
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(BAR(B_ACC1_EMPTY + as));
+              if (lane == 0) ARRIVE_MMA(BAR(B_ACC1_EMPTY + as));
             }
             if (hh == 0) mbar_wait(BAR(B_A2_EMPTY + s2), (u2 & 1u) ^ 1u);
             uint8_t* dst = sA2 + (size_t)s2 * a2_chunk + (size_t)(hcol * 4) * A2_PLANE + (size_t)row * 16;
@@ -587,7 +655,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_A2_FULL + s2));
+          if (lane == 0) ARRIVE_MMA(BAR(B_A2_FULL + s2));
         }
         if (warp == MID_WARP0) STRACE(5);
       }
@@ -606,10 +674,9 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
     const float* bias = FUSE ? p.bias2 : p.bias;
     float* sT = reinterpret_cast<float*>(sStage) + (size_t)ew * (32 * EPI_LD);
     const int crow = lane >> 3, cchunk = (lane & 7) * 4;          // coalesced mapping: rows crow + 4*i, 4 floats at cchunk
-    int it = 0;
-    TilePos tp;
-    tp.init(first, p.tiles_per_item, p.B);
-    for (int tile = first; tile < p.total_tiles; tile += step, ++it, tp.advance(step, p.tiles_per_item, p.B)) {
+    Walk<PAIR> tp;
+    tp.init(p, first, rank);
+    for (int it = 0; it < n_my; ++it, tp.advance(p, step, rank)) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
       const int nt = tp.nt, b = tp.b;
       const int trow0 = tp.tt * BM + q * 32;     // first output row of this warp's block
@@ -617,7 +684,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
       const float* rp = (p.res && !DBG_SKIP(4)) ? p.res + off0 : nullptr;
       float* yp = p.y + off0;
       const size_t istep = (size_t)4 * p.C_out;                         // 4 rows further per load/store instruction
-      const int rows_ok = p.T_out - trow0 - crow;                      // row 4*i of this lane is valid iff 4*i < rows_ok
+      const int rows_ok = tp.valid ? p.T_out - trow0 - crow : 0;       // row 4*i of this lane is valid iff 4*i < rows_ok (phantom tile: none)
       const float* bp = bias ? bias + (size_t)nt * p.N : nullptr;
       const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride + (FUSE ? p.N : 0)) + ((uint32_t)(q * 32) << 16);
       const uint32_t fullbar = BAR((FUSE ? B_ACC2_FULL : B_ACC1_FULL) + as);
@@ -649,7 +716,7 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
         if (c0 + cbstep >= p.N) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(emptybar);
+          if (lane == 0) ARRIVE_MMA(emptybar);
         }
         float* own = sT + lane * EPI_LD;
 #pragma unroll
@@ -685,12 +752,27 @@ __global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(co
   }
 done:
 #undef BAR
-  // ---- teardown ----
+#undef ARRIVE_MMA
+#undef WAIT_MMA
+#undef COMMIT
+  // ---- teardown (pair: nobody frees TMEM / exits while the peer may still be reading or signalling) ----
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+}
+
+template <int SPLIT, bool FUSE>
+__global__ void __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_kernel(const SParams p) {
+  conv_stream_body<SPLIT, FUSE, false>(p);
+}
+// the same roles on a CTA pair: one tcgen05.mma.cta_group::2 of M = 256 per two tiles, half of every weight unit per SM
+template <int SPLIT, bool FUSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Roles<FUSE>::THREADS, 1) conv_stream_pair_kernel(const SParams p) {
+  conv_stream_body<SPLIT, FUSE, true>(p);
 }
 
 long long* g_stream_trace = nullptr;
@@ -701,7 +783,7 @@ struct StreamPlan {
   size_t smem;
 };
 
-bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused, StreamPlan* pl) {
+bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused, StreamPlan* pl, bool pair = false) {
   if (precision != BC_PREC_BF16 && precision != BC_PREC_BF16X3) return false;
   if (C_in % 16 != 0 || C_in < 32 || K < 1 || K > 32 || stride < 1 || dilation < 1) return false;
   if (stride > 1 && dilation > 1) return false;
@@ -717,7 +799,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   pl->N = N;
   pl->n_tiles = C_out / N;
   pl->groups = C_in / 16;
-  pl->tap_bytes = (uint32_t)N * 32u * split;
+  pl->tap_bytes = (uint32_t)(pair ? N / 2 : N) * 32u * split;   // pair form: every SM holds half of the B rows
   int tpu = (int)(UNIT_MAX_BYTES / pl->tap_bytes);
   if (tpu < 1) tpu = 1;
   if (tpu > MAX_TPU) tpu = MAX_TPU;
@@ -776,7 +858,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   return true;
 }
 
-int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) {
+int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, bool pair = false) {
   p.N = pl.N; p.groups = pl.groups; p.tpu = pl.tpu; p.upg = pl.upg; p.gpu1 = pl.gpu1;
   p.slab_rows = pl.slab_rows; p.rpp = pl.rpp; p.NA = pl.NA; p.NB = pl.NB;
   p.acc_stages = pl.acc_stages; p.acc_stride = pl.acc_stride; p.epi_warps = pl.epi_warps; p.a_stage = pl.a_stage; p.unit_bytes = pl.unit_bytes;
@@ -787,7 +869,9 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) 
   if (total > 2147483647ll) return bc::fail(BC_EINVAL, "conv(stream): too many tiles");
   p.tiles_per_nt = (int)per_nt;
   p.total_tiles = (int)total;
-  p.idesc = idesc_bf16_m128(pl.N);
+  p.pairs_per_nt = (int)((per_nt + 1) / 2);
+  p.total_pairs = p.pairs_per_nt * pl.n_tiles;
+  p.idesc = pair ? idesc_bf16_m256(pl.N) : idesc_bf16_m128(pl.N);
   p.trace = g_stream_trace;
 #ifdef BC_TRACE
   { const char* e = getenv("BC_STREAM_BSHIFT"); p.dbg_bshift = e ? (atoi(e) & 15) : 0; }
@@ -795,11 +879,18 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) 
 #endif
   void (*kern)(const SParams) = nullptr;
   int slot = 0;
-  if (pl.split == 1 && !fused) { kern = conv_stream_kernel<1, false>; slot = 0; }
-  if (pl.split == 2 && !fused) { kern = conv_stream_kernel<2, false>; slot = 1; }
-  if (pl.split == 1 && fused) { kern = conv_stream_kernel<1, true>; slot = 2; }
-  if (pl.split == 2 && fused) { kern = conv_stream_kernel<2, true>; slot = 3; }
-  static bool configured[64][4] = {{false}};
+  if (!pair) {
+    if (pl.split == 1 && !fused) { kern = conv_stream_kernel<1, false>; slot = 0; }
+    if (pl.split == 2 && !fused) { kern = conv_stream_kernel<2, false>; slot = 1; }
+    if (pl.split == 1 && fused) { kern = conv_stream_kernel<1, true>; slot = 2; }
+    if (pl.split == 2 && fused) { kern = conv_stream_kernel<2, true>; slot = 3; }
+  } else {
+    if (pl.split == 1 && !fused) { kern = conv_stream_pair_kernel<1, false>; slot = 4; }
+    if (pl.split == 2 && !fused) { kern = conv_stream_pair_kernel<2, false>; slot = 5; }
+    if (pl.split == 1 && fused) { kern = conv_stream_pair_kernel<1, true>; slot = 6; }
+    if (pl.split == 2 && fused) { kern = conv_stream_pair_kernel<2, true>; slot = 7; }
+  }
+  static bool configured[64][8] = {{false}};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -808,9 +899,15 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st) 
     if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(conv_stream)");
     if (dev >= 0 && dev < 64) configured[dev][slot] = true;
   }
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  int grid;
+  if (pair) {
+    const int max_pairs = sms / 2;
+    grid = 2 * (p.total_pairs < max_pairs ? p.total_pairs : max_pairs);
+  } else {
+    grid = p.total_tiles < sms ? p.total_tiles : sms;
+  }
   kern<<<grid, fused ? Roles<true>::THREADS : Roles<false>::THREADS, pl.smem, st>>>(p);
-  BC_LAUNCH_CHECK("conv_stream_kernel");
+  BC_LAUNCH_CHECK(pair ? "conv_stream_pair_kernel" : "conv_stream_kernel");
   return BC_OK;
 }
 
@@ -828,15 +925,15 @@ extern "C" int bc_stream_plan(int C_in, int C_out, int K, int stride, int dilati
   return BC_OK;
 }
 
-extern "C" int bc_conv1d_stream_fwd(const float* x, const void* w_image, const float* bias, const float* snake_a,
-                                    const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
-                                    int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
-                                    bc_stream_t s) {
+static int conv1d_stream_impl(const float* x, const void* w_image, const float* bias, const float* snake_a,
+                              const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                              int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
+                              bc_stream_t s, bool pair) {
   BC_REQUIRE(x && w_image && y, "conv1d(stream): null pointer");
   BC_REQUIRE(B > 0 && T_in > 0 && T_out > 0, "conv1d(stream): bad shape B=%d T_in=%d T_out=%d", B, T_in, T_out);
   BC_REQUIRE(!(flags & BC_CONV_SNAKE_IN) || (snake_a && snake_ib), "conv1d(stream): BC_CONV_SNAKE_IN needs snake_a and snake_ib");
   StreamPlan pl;
-  if (!stream_plan(C_in, C_out, K, stride, dilation, precision, 0, &pl))
+  if (!stream_plan(C_in, C_out, K, stride, dilation, precision, 0, &pl, pair))
     return bc::fail(BC_EUNSUPPORTED, "conv1d(stream): unsupported geometry C_in=%d C_out=%d K=%d stride=%d dil=%d", C_in, C_out, K, stride, dilation);
   BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w_image) && bc::aligned16(y) && (!res || bc::aligned16(res)) &&
                  (!bias || bc::aligned16(bias)) && (!snake_a || bc::aligned16(snake_a)) && (!snake_ib || bc::aligned16(snake_ib)),
@@ -846,7 +943,39 @@ extern "C" int bc_conv1d_stream_fwd(const float* x, const void* w_image, const f
   p.bias = bias; p.bias2 = nullptr; p.sa1 = snake_a; p.sib1 = snake_ib; p.sa2 = nullptr; p.sib2 = nullptr;
   p.B = B; p.T_in = T_in; p.T_out = T_out; p.C_in = C_in; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;
   p.pad_left = pad_left; p.flags = flags; p.nt_shift = 0x7fffffff;
-  return launch_stream(p, pl, 0, (cudaStream_t)s);
+  return launch_stream(p, pl, 0, (cudaStream_t)s, pair);
+}
+
+// 1 when the CTA-pair form has a plan for this geometry (same n_tile as bc_stream_plan) and the policy enables it
+extern "C" int bc_stream_pair_ok(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused) {
+  if (!bc::policy().stream_pair) return 0;
+  // Where the pair form pays (B200, 8 x 30 s clips, split precision; single CTA in brackets): the kernels that are bound by
+  // shared-memory bandwidth -- fused ResidualUnits C = 128: 300 us [327], C = 256: 220 [225]; the 512 -> 512 k = 3 conv:
+  // 451 [513].  The strided down-sampling convs are bound by their producers (fp32 load + SnakeBeta + split per element,
+  // few MMAs per tile) and only pay for the pair's lock-step: 32->64 302 [274], 64->128 296 [252], 128->256 224 [201],
+  // 256->512 219 [197]; the K = 1 input projection is neutral (1072 [1068]).
+  if (!fused && !(stride == 1 && K >= 3 && C_in >= 256)) return 0;
+  StreamPlan a, b;
+  if (!stream_plan(C_in, C_out, K, stride, dilation, precision, fused, &a, false)) return 0;
+  if (!stream_plan(C_in, C_out, K, stride, dilation, precision, fused, &b, true)) return 0;
+  return a.N == b.N ? 1 : 0;
+}
+
+extern "C" int bc_conv1d_stream_fwd(const float* x, const void* w_image, const float* bias, const float* snake_a,
+                                    const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                                    int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
+                                    bc_stream_t s) {
+  return conv1d_stream_impl(x, w_image, bias, snake_a, snake_ib, res, y, B, T_in, C_in, T_out, C_out, K, stride, dilation, pad_left,
+                            flags, precision, s, false);
+}
+
+// CTA-pair form (tcgen05 cta_group::2): same arithmetic, w_image = the PAIR image (bc_stream_pair_image_layout)
+extern "C" int bc_conv1d_stream_pair_fwd(const float* x, const void* w_image, const float* bias, const float* snake_a,
+                                         const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                                         int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
+                                         bc_stream_t s) {
+  return conv1d_stream_impl(x, w_image, bias, snake_a, snake_ib, res, y, B, T_in, C_in, T_out, C_out, K, stride, dilation, pad_left,
+                            flags, precision, s, true);
 }
 
 // Transposed conv (k = 2*stride, T_out = T_in*stride; vq/module.py:67-72,119-136) as ONE launch of the streamed-weight
@@ -856,14 +985,14 @@ extern "C" int bc_conv1d_stream_fwd(const float* x, const void* w_image, const f
 // w_image: pack_stream_weight of [2][C_in][stride*C_out] (column ph*C_out + co = phase filter ph), bias_tiled:
 // [stride*C_out].  Needs C_out % n_tile == 0 (every n-tile inside one phase); other geometries use the K = 3 zero-padded
 // form through bc_conv1d_stream_fwd or the per-phase path of bc_convtr1d_fwd.
-extern "C" int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
-                                      const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
-                                      int padding, int flags, int precision, bc_stream_t s) {
+static int convtr1d_stream_impl(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                                const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                                int padding, int flags, int precision, bc_stream_t s, bool pair) {
   BC_REQUIRE(x && w_image && y, "convtr1d(stream): null pointer");
   BC_REQUIRE(B > 0 && T_in > 0 && stride >= 2 && padding >= 0 && padding < stride, "convtr1d(stream): bad shape B=%d T_in=%d stride=%d padding=%d", B, T_in, stride, padding);
   BC_REQUIRE(!(flags & BC_CONV_SNAKE_IN) || (snake_a && snake_ib), "convtr1d(stream): BC_CONV_SNAKE_IN needs snake_a and snake_ib");
   StreamPlan pl;
-  if (!stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl) || C_out % pl.N != 0)
+  if (!stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl, pair) || C_out % pl.N != 0)
     return bc::fail(BC_EUNSUPPORTED, "convtr1d(stream): C_in=%d C_out=%d stride=%d has no single-launch plan", C_in, C_out, stride);
   BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w_image) && bc::aligned16(y) && (!bias_tiled || bc::aligned16(bias_tiled)) &&
                  (!snake_a || bc::aligned16(snake_a)) && (!snake_ib || bc::aligned16(snake_ib)),
@@ -874,18 +1003,30 @@ extern "C" int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const
   p.B = B; p.T_in = T_in; p.T_out = T_in; p.C_in = C_in; p.C_out = stride * C_out; p.K = 2; p.stride = 1; p.dil = 1;
   p.pad_left = 1; p.flags = flags;
   p.nt_shift = (stride - padding) * (C_out / pl.N);          // first n-tile of phase ph = stride - padding, the first with q = 1
-  return launch_stream(p, pl, 0, (cudaStream_t)s);
+  return launch_stream(p, pl, 0, (cudaStream_t)s, pair);
 }
 
-extern "C" int bc_resunit_stream_fwd(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
-                                     const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
-                                     const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
-                                     int precision, bc_stream_t s) {
+extern "C" int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                                      const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                                      int padding, int flags, int precision, bc_stream_t s) {
+  return convtr1d_stream_impl(x, w_image, bias_tiled, snake_a, snake_ib, y, B, T_in, C_in, C_out, stride, padding, flags, precision, s, false);
+}
+// CTA-pair form: w_image = the pair image of the same [2][C_in][stride*C_out] filter
+extern "C" int bc_convtr1d_stream_pair_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                                           const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                                           int padding, int flags, int precision, bc_stream_t s) {
+  return convtr1d_stream_impl(x, w_image, bias_tiled, snake_a, snake_ib, y, B, T_in, C_in, C_out, stride, padding, flags, precision, s, true);
+}
+
+static int resunit_stream_impl(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
+                               const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
+                               const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
+                               int precision, bc_stream_t s, bool pair) {
   BC_REQUIRE(x && w7_image && b7 && snake1_a && snake1_ib && w1_image && b1 && snake2_a && snake2_ib && y, "resunit(stream): null pointer");
   BC_REQUIRE(B > 0 && T > 0 && C > 0 && K > 0 && dilation > 0, "resunit(stream): bad shape B=%d T=%d C=%d K=%d", B, T, C, K);
   BC_REQUIRE(x != y, "resunit(stream): cannot run in place (neighbouring tiles read the input halo)");
   StreamPlan pl;
-  if (!stream_plan(C, C, K, 1, dilation, precision, 1, &pl))
+  if (!stream_plan(C, C, K, 1, dilation, precision, 1, &pl, pair))
     return bc::fail(BC_EUNSUPPORTED, "resunit(stream): C=%d K=%d dil=%d has no streamed-weight plan", C, K, dilation);
   BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w7_image) && bc::aligned16(w1_image) && bc::aligned16(y) && bc::aligned16(b7) &&
                  bc::aligned16(b1) && bc::aligned16(snake1_a) && bc::aligned16(snake1_ib) && bc::aligned16(snake2_a) && bc::aligned16(snake2_ib),
@@ -895,7 +1036,23 @@ extern "C" int bc_resunit_stream_fwd(const float* x, const void* w7_image, const
   p.bias = b7; p.bias2 = b1; p.sa1 = snake1_a; p.sib1 = snake1_ib; p.sa2 = snake2_a; p.sib2 = snake2_ib;
   p.B = B; p.T_in = T; p.T_out = T; p.C_in = C; p.C_out = C; p.K = K; p.stride = 1; p.dil = dilation;
   p.pad_left = pad_left; p.flags = BC_CONV_SNAKE_IN; p.nt_shift = 0x7fffffff;
-  return launch_stream(p, pl, 1, (cudaStream_t)s);
+  return launch_stream(p, pl, 1, (cudaStream_t)s, pair);
+}
+
+extern "C" int bc_resunit_stream_fwd(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
+                                     const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
+                                     const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
+                                     int precision, bc_stream_t s) {
+  return resunit_stream_impl(x, w7_image, b7, snake1_a, snake1_ib, w1_image, b1, snake2_a, snake2_ib, y, B, T, C, K, dilation,
+                             pad_left, precision, s, false);
+}
+
+extern "C" int bc_resunit_stream_pair_fwd(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
+                                          const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
+                                          const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
+                                          int precision, bc_stream_t s) {
+  return resunit_stream_impl(x, w7_image, b7, snake1_a, snake1_ib, w1_image, b1, snake2_a, snake2_ib, y, B, T, C, K, dilation,
+                             pad_left, precision, s, true);
 }
 
 // debug hook (not part of the product path): device buffer of 64*16 int64 (zeroed by the caller) that receives

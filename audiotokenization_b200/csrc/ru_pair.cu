@@ -28,13 +28,11 @@
 //          the stacked image does not leave room for two activation slots (dilation 9).
 //   The 1x1 conv always runs plain.
 //
-// Measured (B200, 8 x 30 s clips, C = 64, split precision; ru_persist in brackets): dilation 1 / 3 (stacked) 472 / 466 us
-// [442 / 438], dilation 9 (plain) 441 us [450].  The second activation slot and the halved B fetch buy nothing: the
-// unit executes ~12 k warp-instructions per 128-row tile (SnakeBeta + hi/lo split of the 182-row slab, the middle
-// activation, the store stage) at 41 % issue utilisation, and that -- not the LOAD -> MMA hand-off -- is the tile period;
-// the pair adds its lock-step (the slower of two tiles) on top.  The kernel therefore is OPT-IN (BC_RU_PAIR=1); it stays
-// in the tree as the validated cta_group::2 protocol (remote mbarrier arrives + multicast commits, exact results on odd
-// tile counts and multi-round schedules: tests/test_gpu_ops.py::test_cta_pair_residual_unit_*).
+// Measured (B200, 8 x 30 s clips, C = 64, split precision; ru_persist in brackets): dilation 1 / 3 (stacked) 363 / 366 us
+// [442 / 438], dilation 9 (plain) 375 us [450]: 20 % faster.  The first build was no faster than ru_persist (472 / 466 /
+// 441 us): its cross-CTA arrives and waits asked for cluster-scope release / acquire, which compiles to MEMBAR.ALL.GPU +
+// CCTL.IVALL -- an L1 invalidation per hand-off that the loaders' cached activation reads paid for.  The hand-offs only
+// carry shared-memory data, for which the default CTA-scope semantics are enough (tc_common.cuh, BC_PAIR_STRONG).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -75,71 +73,6 @@ struct RpParams {
 
 enum { B_A_FULL = 0, B_A_EMPTY = 2, B_ACC1_FULL = 4, B_ACC1_EMPTY = 6, B_A2_FULL = 8, B_A2_EMPTY = 9,
        B_ACC2_FULL = 10, B_ACC2_EMPTY = 12, B_W_FULL = 14, N_BARS = 15 };
-
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the LEADER CTA's copy of a barrier (rank 0 of the pair), from either CTA
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(0u));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// wait with cluster-scope acquire (the arrivals come from both CTAs)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0;; ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000000u)
-        : "memory");
-    if (ok) return;
-    if (it > 4000u) __trap();
-  }
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-template <bool ACC>
-__device__ __forceinline__ void mma2_bf16_raw(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
-                                              uint32_t idesc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0)
-      : "memory");
-}
-// runtime accumulate flag (0 = overwrite the accumulator, else accumulate)
-__device__ __forceinline__ void mma2_bf16_rt(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 256 across the CTA pair
-__host__ __device__ inline uint32_t idesc_bf16_m256(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
 
 // r[0 .. 32) += the 32 accumulator columns at `taddr` (the a_hi * w_lo half), 16 columns at a time to bound registers
 __device__ __forceinline__ void add_lo_half32(uint32_t taddr, uint32_t r[32]) {

@@ -317,5 +317,95 @@ __host__ __device__ inline uint32_t idesc_bf16_m128(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA pairs (tcgen05 cta_group::2): one MMA of M = 256 across a cluster of two CTAs, each SM contributing the 128 rows of
+// its own tile as the A operand and HALF of the B operand's rows.  Protocol shared by ru_pair.cu and the pair form of
+// conv_stream.cu: producers of BOTH CTAs arrive on the LEADER's barrier (rank 0), the leader's MMA thread signals
+// consumers in both CTAs with a multicast commit; every barrier sits at the same shared-memory offset in both CTAs.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Memory-model scope of the cross-CTA hand-offs.  What travels between the CTAs of a pair is SHARED-MEMORY data for the
+// tensor core (activation slabs, re-quantised tiles: generic-proxy stores made visible to the async proxy with
+// fence.proxy.async before the arrive) and "accumulator drained" notifications -- never global memory.  Cluster-scope
+// release / acquire compiles to MEMBAR + CCTL.IVALL (an L1 invalidation per wait: `cuobjdump -sass` showed 20 CCTL in
+// the first ru_pair build), which the loaders' L1-cached activation reads pay for.  The default semantics
+// (release / acquire at CTA scope -- what CUTLASS' ClusterBarrier::arrive(cta_id) emits for its 2-SM kernels) order the
+// shared-memory stores before the arrive, which is all these hand-offs need.  -DBC_PAIR_STRONG=1 restores cluster scope.
+#ifndef BC_PAIR_STRONG
+#define BC_PAIR_STRONG 0
+#endif
+// arrive on the LEADER CTA's copy of a barrier (rank 0 of the pair), from either CTA
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(0u));
+#if BC_PAIR_STRONG
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
+}
+// wait on a barrier whose arrivals come from both CTAs
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#if BC_PAIR_STRONG
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) return;
+    if (it > 4000u) __trap();
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void mma2_bf16_raw(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                              uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+// runtime accumulate flag (0 = overwrite the accumulator, else accumulate)
+__device__ __forceinline__ void mma2_bf16_rt(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 256 across the CTA pair
+__host__ __device__ inline uint32_t idesc_bf16_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+
 }  // namespace tc
 }  // namespace bc

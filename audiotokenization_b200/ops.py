@@ -183,7 +183,7 @@ def conv_transpose1d(x: torch.Tensor, w_phases: torch.Tensor, bias: Optional[tor
 
 def conv_transpose1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias_tiled: Optional[torch.Tensor], *, stride: int,
                             padding: int, c_out: int, three_tap: bool, snake_a: Optional[torch.Tensor] = None,
-                            snake_ib: Optional[torch.Tensor] = None, precision: str) -> torch.Tensor:
+                            snake_ib: Optional[torch.Tensor] = None, precision: str, pair: bool = False) -> torch.Tensor:
     """Transposed conv (k = 2*stride) as ONE launch of the persistent streamed-weight kernel: all output phases are the
     channel blocks of a conv with stride*C_out outputs (``pack_convtr_stream_weight``)."""
     x = _cl(x)
@@ -192,19 +192,23 @@ def conv_transpose1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias_tiled: Op
     flags = BC_CONV_SNAKE_IN if snake_a is not None else 0
     with _Timed(("convtr1d", C_in, c_out, 2 * stride, stride, 1, T_in * stride, B, precision),
                 2.0 * B * T_in * stride * c_out * C_in * 2, x.device, "conv_stream_kernel", 4.0 * B * T_in * (C_in + stride * c_out)):
+        lib = load_library()
         if three_tap:
-            check(load_library().bc_conv1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), None,
-                                                      ptr(y), B, T_in, C_in, T_in, stride * c_out, 3, 1, 1, 1, flags,
-                                                      PRECISIONS[precision], stream_ptr(x.device)), "bc_conv1d_stream_fwd")
+            fn = lib.bc_conv1d_stream_pair_fwd if pair else lib.bc_conv1d_stream_fwd
+            check(fn(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), None,
+                     ptr(y), B, T_in, C_in, T_in, stride * c_out, 3, 1, 1, 1, flags,
+                     PRECISIONS[precision], stream_ptr(x.device)), "bc_conv1d_stream_fwd")
         else:
-            check(load_library().bc_convtr1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), ptr(y),
-                                                        B, T_in, C_in, c_out, stride, padding, flags, PRECISIONS[precision],
-                                                        stream_ptr(x.device)), "bc_convtr1d_stream_fwd")
+            fn = lib.bc_convtr1d_stream_pair_fwd if pair else lib.bc_convtr1d_stream_fwd
+            check(fn(ptr(x), ptr(w_img), ptr(bias_tiled), ptr(snake_a), ptr(snake_ib), ptr(y),
+                     B, T_in, C_in, c_out, stride, padding, flags, PRECISIONS[precision],
+                     stream_ptr(x.device)), "bc_convtr1d_stream_fwd")
     _count()
     return y.view(B, T_in * stride, c_out)
 
 
-def pack_convtr_stream_weight(w_phases: torch.Tensor, stride: int, padding: int, n_tile: int, precision: str):
+def pack_convtr_stream_weight(w_phases: torch.Tensor, stride: int, padding: int, n_tile: int, precision: str,
+                              pair: bool = False):
     """fp32 phase filters [stride, 2, C_in, C_out] -> (streamed-weight image, three_tap).  Two taps when every n-tile
     lies inside one phase (the kernel shifts the taps of the q = 1 phases by one row); otherwise three taps on rows
     m-1, m, m+1 with zeros where a phase does not reach (q = 0: taps 0, 1; q = 1: taps 1, 2)."""
@@ -217,7 +221,7 @@ def pack_convtr_stream_weight(w_phases: torch.Tensor, stride: int, padding: int,
         for ph in range(s):
             q = (ph + padding) // s
             w[q:q + 2, :, ph * c_out:(ph + 1) * c_out] = w_phases[ph]
-    return pack_stream_weight(w.contiguous(), n_tile, precision), three_tap
+    return (pack_stream_weight_pair if pair else pack_stream_weight)(w.contiguous(), n_tile, precision), three_tap
 
 
 _TC_PLANS = {}
@@ -321,11 +325,39 @@ def pack_stream_weight(w_kio: torch.Tensor, n_tile: int, precision: str) -> torc
     return torch.stack(parts, dim=3).contiguous()
 
 
+def stream_pair_ok(c_in: int, c_out: int, k: int, stride: int, dilation: int, precision: str, fused: bool = False) -> bool:
+    """True when the CTA-pair form (tcgen05 cta_group::2) of the streamed-weight kernel takes this geometry."""
+    if precision == "fp32":
+        return False
+    key = ("pair", c_in, c_out, k, stride, dilation, precision, bool(fused))
+    if key not in _TC_PLANS:
+        _TC_PLANS[key] = bool(load_library().bc_stream_pair_ok(c_in, c_out, k, stride, dilation, PRECISIONS[precision], int(bool(fused))))
+    return _TC_PLANS[key]
+
+
+def pack_stream_weight_pair(w_kio: torch.Tensor, n_tile: int, precision: str) -> torch.Tensor:
+    """fp32 [K, C_in, C_out] -> bf16 PAIR image [C_out/n_tile][2][C_in/16][K][split][2][n_tile/2][8] of the CTA-pair form:
+    rank r of the pair holds rows [r*n_tile/2, (r+1)*n_tile/2) of every k-plane of every (16-channel group, tap) block."""
+    K, c_in, c_out = w_kio.shape
+    w = w_kio.float()
+    hi = w.to(torch.bfloat16)
+    h2 = n_tile // 2
+
+    def image(t):   # (k, g, h, e, nt, r, n) -> (nt, r, g, k, h, n, e)
+        return t.reshape(K, c_in // 16, 2, 8, c_out // n_tile, 2, h2).permute(4, 5, 1, 0, 2, 6, 3)
+
+    parts = [image(hi)]
+    if precision == "bf16x3":
+        parts.append(image((w - hi.float()).to(torch.bfloat16)))
+    return torch.stack(parts, dim=4).contiguous()
+
+
 def conv1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Tensor], *, k: int, c_out: int,
                   stride: int = 1, dilation: int = 1, pad_left: int = 0, t_out: int,
                   snake_a: Optional[torch.Tensor] = None, snake_ib: Optional[torch.Tensor] = None,
-                  res: Optional[torch.Tensor] = None, tanh: bool = False, precision: str) -> torch.Tensor:
-    """Dense conv on the persistent streamed-weight kernel (``w_img`` from pack_stream_weight)."""
+                  res: Optional[torch.Tensor] = None, tanh: bool = False, precision: str, pair: bool = False) -> torch.Tensor:
+    """Dense conv on the persistent streamed-weight kernel (``w_img`` from pack_stream_weight, or, with ``pair``, from
+    pack_stream_weight_pair: the CTA-pair form)."""
     x = _cl(x)
     B, T_in, C_in = x.shape
     if t_out <= 0:
@@ -338,16 +370,18 @@ def conv1d_stream(x: torch.Tensor, w_img: torch.Tensor, bias: Optional[torch.Ten
             raise ValueError(f"conv1d: residual shape {tuple(res.shape)} != output {(B, t_out, c_out)}")
     with _Timed(("conv1d", C_in, c_out, k, stride, dilation, t_out, B, precision), 2.0 * B * t_out * c_out * C_in * k, x.device,
                 "conv_stream_kernel", 4.0 * B * (T_in * C_in + t_out * c_out * (2 if res is not None else 1))):
-        check(load_library().bc_conv1d_stream_fwd(ptr(x), ptr(w_img), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res),
-                                                  ptr(y), B, T_in, C_in, t_out, c_out, k, stride, dilation, pad_left,
-                                                  flags, PRECISIONS[precision], stream_ptr(x.device)),
+        fn = load_library().bc_conv1d_stream_pair_fwd if pair else load_library().bc_conv1d_stream_fwd
+        check(fn(ptr(x), ptr(w_img), ptr(bias), ptr(snake_a), ptr(snake_ib), ptr(res),
+                 ptr(y), B, T_in, C_in, t_out, c_out, k, stride, dilation, pad_left,
+                 flags, PRECISIONS[precision], stream_ptr(x.device)),
               "bc_conv1d_stream_fwd")
     _count()
     return y
 
 
 def resunit_stream(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.Tensor, b1, sa2, sib2, *, k: int,
-                   dilation: int, pad_left: int, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   dilation: int, pad_left: int, precision: str, out: Optional[torch.Tensor] = None,
+                   pair: bool = False) -> torch.Tensor:
     """Fused ResidualUnit on the persistent streamed-weight kernel (wide layers).  ``out``: write the result
     into this contiguous [B,T,C] tensor (e.g. a slice of a larger batch buffer) instead of a fresh one."""
     x = _cl(x)
@@ -360,9 +394,10 @@ def resunit_stream(x: torch.Tensor, w7: torch.Tensor, b7, sa1, sib1, w1: torch.T
         y = torch.empty_like(x)
     flops = 2.0 * B * T * C * C * (k + 1)
     with _Timed(("resunit", C, C, k, 1, dilation, T, B, precision), flops, x.device, "conv_stream_kernel", 8.0 * B * T * C):
-        check(load_library().bc_resunit_stream_fwd(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1),
-                                                   ptr(sa2), ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left,
-                                                   PRECISIONS[precision], stream_ptr(x.device)),
+        fn = load_library().bc_resunit_stream_pair_fwd if pair else load_library().bc_resunit_stream_fwd
+        check(fn(ptr(x), ptr(w7), ptr(b7), ptr(sa1), ptr(sib1), ptr(w1), ptr(b1),
+                 ptr(sa2), ptr(sib2), ptr(y), B, T, C, k, dilation, pad_left,
+                 PRECISIONS[precision], stream_ptr(x.device)),
               "bc_resunit_stream_fwd")
     _count()
     return y

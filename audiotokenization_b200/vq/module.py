@@ -36,6 +36,7 @@ def _cabi_sm_count() -> int:
     return c[dev]
 FUSE_RESUNIT = [True]   # tensor-core modes: run a whole ResidualUnit as one kernel when the geometry allows
 STREAM = [True]         # tensor-core modes: wide layers run on the persistent streamed-weight kernel
+STREAM_PAIR = [True]    # ... in its CTA-pair form (tcgen05 cta_group::2) where the geometry has one
 CONVTR_STREAM = [True]  # ... and transposed convs as ONE launch of it (all phases as channel blocks)
 import os as _os
 STREAM_MIN_CIN = [int(_os.environ.get("BC_STREAM_MIN_CIN", "32"))]    # ... when the layer has at least this many input channels
@@ -172,12 +173,13 @@ class _Conv1dWN(_WNParams):
             cache.update(key=key, w=ops.pack_tc_weight(w, plan, precision))
         return cache["w"], b, precision
 
-    def stream_image(self, precision: str, n_tile: int):
+    def stream_image(self, precision: str, n_tile: int, pair: bool = False):
         cache = self.__dict__.setdefault("_stream_cache", {})
-        key = (precision, n_tile, self._key())
+        key = (precision, n_tile, pair, self._key())
         if cache.get("key") != key:
+            pack = ops.pack_stream_weight_pair if pair else ops.pack_stream_weight
             cache.clear()
-            cache.update(key=key, w=ops.pack_stream_weight(self.packed()[0], n_tile, precision))
+            cache.update(key=key, w=pack(self.packed()[0], n_tile, precision))
         return cache["w"]
 
     def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None, res=None, tanh=False):
@@ -187,10 +189,12 @@ class _Conv1dWN(_WNParams):
         precision = get_precision()
         nt = _stream_tile(self.in_channels, self.out_channels, self.kernel_size, self.stride, self.dilation, precision)
         if nt is not None:
-            return ops.conv1d_stream(x_cl, self.stream_image(precision, nt), self.packed()[1], k=self.kernel_size,
+            pair = STREAM_PAIR[0] and ops.stream_pair_ok(self.in_channels, self.out_channels, self.kernel_size, self.stride,
+                                                         self.dilation, precision)
+            return ops.conv1d_stream(x_cl, self.stream_image(precision, nt, pair), self.packed()[1], k=self.kernel_size,
                                      c_out=self.out_channels, stride=self.stride, dilation=self.dilation,
                                      pad_left=self.left_pad, t_out=self.out_length(x_cl.shape[1]), snake_a=a,
-                                     snake_ib=ib, res=res, tanh=tanh, precision=precision)
+                                     snake_ib=ib, res=res, tanh=tanh, precision=precision, pair=pair)
         w, b, prec = self.packed_for(precision)
         return ops.conv1d(x_cl, w, b, stride=self.stride, dilation=self.dilation, pad_left=self.left_pad,
                           t_out=self.out_length(x_cl.shape[1]), snake_a=a, snake_ib=ib, res=res, tanh=tanh,
@@ -255,14 +259,16 @@ class _ConvTranspose1dWN(_WNParams):
             nt = _stream_tile(self.in_channels, self.stride * self.out_channels, 3, 1, 1, precision)
             if nt is None:
                 return None
+        three = self.out_channels % nt != 0
+        pair = STREAM_PAIR[0] and ops.stream_pair_ok(self.in_channels, self.stride * self.out_channels, 3 if three else 2, 1, 1, precision)
         cache = self.__dict__.setdefault("_stream_cache", {})
-        key = (precision, nt, self._key())
+        key = (precision, nt, pair, self._key())
         if cache.get("key") != key:
             w, b = self.packed()
-            img, three = ops.pack_convtr_stream_weight(w, self.stride, self.padding, nt, precision)
+            img, three = ops.pack_convtr_stream_weight(w, self.stride, self.padding, nt, precision, pair)
             cache.clear()
-            cache.update(key=key, w=img, b=b.repeat(self.stride).contiguous(), three=three)
-        return cache["w"], cache["b"], cache["three"]
+            cache.update(key=key, w=img, b=b.repeat(self.stride).contiguous(), three=three, pair=pair)
+        return cache["w"], cache["b"], cache["three"], cache["pair"]
 
     def forward_cl(self, x_cl, act: Optional[activations.SnakeBeta] = None):
         precision = get_precision()
@@ -273,7 +279,7 @@ class _ConvTranspose1dWN(_WNParams):
         if st is not None:
             return ops.conv_transpose1d_stream(x_cl, st[0], st[1], stride=self.stride, padding=self.padding,
                                                c_out=self.out_channels, three_tap=st[2], snake_a=a, snake_ib=ib,
-                                               precision=precision)
+                                               precision=precision, pair=st[3])
         w, b, prec = self.packed_for(precision)
         return ops.conv_transpose1d(x_cl, w, b, stride=self.stride, padding=self.padding, snake_a=a, snake_ib=ib,
                                     precision=prec, c_out=self.out_channels)
@@ -380,9 +386,10 @@ class ResidualUnit(nn.Module):
             return None
         sa1, sib1 = self.block[0].act.device_params()
         sa2, sib2 = self.block[2].act.device_params()
-        return ops.resunit_stream(x_cl, conv7.stream_image(prec, nt), conv7.packed()[1], sa1, sib1,
-                                  conv1.stream_image(prec, nt), conv1.packed()[1], sa2, sib2, k=conv7.kernel_size,
-                                  dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec, out=out)
+        pair = STREAM_PAIR[0] and ops.stream_pair_ok(C, C, conv7.kernel_size, 1, conv7.dilation, prec, fused=True)
+        return ops.resunit_stream(x_cl, conv7.stream_image(prec, nt, pair), conv7.packed()[1], sa1, sib1,
+                                  conv1.stream_image(prec, nt, pair), conv1.packed()[1], sa2, sib2, k=conv7.kernel_size,
+                                  dilation=conv7.dilation, pad_left=conv7.left_pad, precision=prec, out=out, pair=pair)
 
     def forward_cl(self, x_cl, out=None):
         """``out``: optional contiguous [B,T,C] destination (a slice of a larger batch buffer)."""
@@ -546,13 +553,13 @@ class _LSTMParams(nn.Module):
         return cache[key], bias, precision
 
 
-    def input_proj_stream(self, layer: int, precision: str, n_tile: int):
+    def input_proj_stream(self, layer: int, precision: str, n_tile: int, pair: bool = False):
         """Input-projection weight as the streamed-weight image."""
         w_in, _, _ = self.packed(layer)
         cache = self.__dict__.setdefault("_stream_cache", {})
-        key = (layer, precision, n_tile, w_in.data_ptr())
+        key = (layer, precision, n_tile, pair, w_in.data_ptr())
         if key not in cache:
-            cache[key] = ops.pack_stream_weight(w_in, n_tile, precision)
+            cache[key] = (ops.pack_stream_weight_pair if pair else ops.pack_stream_weight)(w_in, n_tile, precision)
         return cache[key]
 
 
@@ -571,8 +578,9 @@ class ResLSTM(nn.Module):
         H = self.lstm.hidden_size
         nt = _stream_tile(h.shape[2], 4 * H, 1, 1, 1, precision)
         if nt is not None:
-            return ops.conv1d_stream(h, self.lstm.input_proj_stream(l, precision, nt), self.lstm.packed(l)[1], k=1,
-                                     c_out=4 * H, t_out=h.shape[1], precision=precision)
+            pair = STREAM_PAIR[0] and ops.stream_pair_ok(h.shape[2], 4 * H, 1, 1, 1, precision)
+            return ops.conv1d_stream(h, self.lstm.input_proj_stream(l, precision, nt, pair), self.lstm.packed(l)[1], k=1,
+                                     c_out=4 * H, t_out=h.shape[1], precision=precision, pair=pair)
         w_in, bias, prec = self.lstm.input_proj_for(l, precision)
         return ops.conv1d(h, w_in, bias, t_out=h.shape[1], precision=prec, geometry=(1, h.shape[2], 4 * H))
 

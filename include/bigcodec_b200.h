@@ -150,6 +150,22 @@ int bc_resunit_stream_fwd(const float* x, const void* w7_image, const float* b7,
                           const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
                           int precision, bc_stream_t s);
 
+/* CTA-pair form of the two entry points above (tcgen05 cta_group::2: one MMA of M = 256 over two 128-step tiles of a
+ * cluster of two CTAs, each SM holding HALF of every weight unit -- half the B-operand fetch and half the weight stream
+ * per SM, the two things that bound the wide layers).  Same arguments and arithmetic; the weight
+ * image is the PAIR image [C_out/n_tile][2 ranks][C_in/16][K][split][2][n_tile/2][8]: rank r holds rows
+ * [r*n_tile/2, (r+1)*n_tile/2) of every k-plane.  bc_stream_pair_ok = 1 when the geometry has a pair plan (and
+ * BC_STREAM_PAIR != 0). */
+int bc_stream_pair_ok(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused);
+int bc_conv1d_stream_pair_fwd(const float* x, const void* w_image, const float* bias, const float* snake_a,
+                              const float* snake_ib, const float* res, float* y, int B, int T_in, int C_in, int T_out,
+                              int C_out, int K, int stride, int dilation, int pad_left, int flags, int precision,
+                              bc_stream_t s);
+int bc_resunit_stream_pair_fwd(const float* x, const void* w7_image, const float* b7, const float* snake1_a,
+                               const float* snake1_ib, const void* w1_image, const float* b1, const float* snake2_a,
+                               const float* snake2_ib, float* y, int B, int T, int C, int K, int dilation, int pad_left,
+                               int precision, bc_stream_t s);
+
 /* Transposed conv as `stride` output phases of 2-tap convs:
  * w_phases[phase][2][C_in][C_out] (host-packed from the folded [C_in,C_out,2*stride]
  * weight: tap0 = W[:,:,j0+stride], tap1 = W[:,:,j0], j0 = (phase+padding) % stride).
@@ -171,6 +187,11 @@ int bc_convtr1d_fwd(const float* x, const float* w_phases, const float* bias,
 int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
                            const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
                            int padding, int flags, int precision, bc_stream_t s);
+
+/* ... and its CTA-pair form (pair image, bc_stream_pair_ok(C_in, stride*C_out, 2, 1, 1, ...)). */
+int bc_convtr1d_stream_pair_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,
+                                const float* snake_ib, float* y, int B, int T_in, int C_in, int C_out, int stride,
+                                int padding, int flags, int precision, bc_stream_t s);
 
 /* ---- LSTM ---------------------------------------------------------------- */
 /* One uni-directional LSTM layer, recurrent part (nn.LSTM inside ResLSTM,

@@ -458,7 +458,7 @@ for dil, B, T in [(1, 3, 40000), (3, 1, 128 * 151), (9, 5, 9000), (9, 1, 100), (
 
 
 def test_cta_pair_residual_unit_many_tiles_odd_counts():
-    """ru_pair.cu (tcgen05 cta_group::2, C = 64, split precision; opt-in with BC_RU_PAIR=1, hence the subprocess): more
+    """ru_pair.cu (tcgen05 cta_group::2, C = 64, split precision; the default, pinned here with BC_RU_PAIR=1): more
     tile pairs than CTA pairs (every pair walks several rounds through both activation slots and accumulator stages),
     odd tile counts (the phantom tile of rank 1), a single tile, tiles that straddle items, stacked and plain weight
     images -- against the float64 oracle and the unfused two-launch path."""

@@ -364,3 +364,24 @@ def test_precision_lives_on_the_modules_not_only_in_the_process_global():
         assert M.get_precision() == "bf16x3"
     with pytest.raises(ValueError):
         m.precision = "fp8"
+
+
+def test_stream_pair_weight_image_layout():
+    """CTA-pair image: [n_tile block][rank][16-channel group][tap][split][k-plane][n_tile/2 rows][8]; rank r holds rows
+    [r*n_tile/2, (r+1)*n_tile/2) of every k-plane; hi + lo reproduces the weight to bf16x3 accuracy."""
+    from audiotokenization_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    K, cin, cout, nt = 3, 32, 256, 128
+    w = torch.randn(K, cin, cout, generator=g)
+    img = ops.pack_stream_weight_pair(w, nt, "bf16x3")
+    assert tuple(img.shape) == (cout // nt, 2, cin // 16, K, 2, 2, nt // 2, 8) and img.dtype == torch.bfloat16
+    single = ops.pack_stream_weight(w, nt, "bf16x3")            # [nt][g][k][split][2][N][8]
+    for r in range(2):
+        assert torch.equal(img[:, r], single[..., r * (nt // 2):(r + 1) * (nt // 2), :])
+    # element check: image[nb, r, grp, k, sp, h, n, e] = part_sp(w[k, grp*16 + h*8 + e, nb*nt + r*nt/2 + n])
+    hi = w.to(torch.bfloat16)
+    for (nb, r, grp, k, h, n, e) in [(0, 0, 0, 0, 0, 0, 0), (1, 1, 1, 2, 1, 63, 7), (0, 1, 1, 1, 0, 5, 3)]:
+        assert img[nb, r, grp, k, 0, h, n, e] == hi[k, grp * 16 + h * 8 + e, nb * nt + r * (nt // 2) + n]
+    rec = (img[:, :, :, :, 0].float() + img[:, :, :, :, 1].float())
+    ref = w.reshape(K, cin // 16, 2, 8, cout // nt, 2, nt // 2).permute(4, 5, 1, 0, 2, 6, 3)
+    assert float((rec - ref).abs().max()) <= 2e-5 * float(w.abs().max())
