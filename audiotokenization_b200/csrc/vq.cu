@@ -60,19 +60,19 @@ __device__ __forceinline__ void top2_merge(Top2& a, float v1, float v2, int i1) 
 // D = 8: register-tiled scan over a shared-memory-resident codebook tile
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SC_THREADS = 256;
-constexpr int SC_FR = 8;                         // frames per thread
-constexpr int SC_FRAMES = SC_THREADS * SC_FR;    // frames per CTA
+constexpr int SC_FR_MAX = 8;                     // frames per thread: 8 (large inputs) or 2 (fewer than one wave of 2048-frame CTAs)
 constexpr int SC_TK = 512;                       // codes per shared-memory tile
 constexpr int SC_D = 8;
-constexpr size_t SC_SMEM = (size_t)SC_FRAMES * SC_D * sizeof(float);   // 64 KB: projected frames, then two duplicated code tiles
+constexpr size_t SC_SMEM = (size_t)SC_THREADS * SC_FR_MAX * SC_D * sizeof(float);   // 64 KB: projected frames, then two duplicated code tiles
 
-template <bool MARGIN>
+template <bool MARGIN, int SC_FR>
 __global__ void __launch_bounds__(SC_THREADS, 2) vq_scan_kernel(const float* __restrict__ z, const float* __restrict__ w_in,
                                                                 const float* __restrict__ b_in, const float* __restrict__ cbn,
                                                                 int32_t* __restrict__ idx, float* __restrict__ margin,
                                                                 float* __restrict__ z_e_out, int N, int C, int Kc) {
   extern __shared__ __align__(16) float smem[];
   constexpr int D = SC_D;
+  constexpr int SC_FRAMES = SC_THREADS * SC_FR;    // frames per CTA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_base = (long long)blockIdx.x * SC_FRAMES;
   const int n_here = (int)min((long long)SC_FRAMES, (long long)N - n_base);
@@ -480,21 +480,36 @@ extern "C" int bc_vq_encode(const float* z, const float* w_in, const float* b_in
   if (!w_in) BC_REQUIRE(C == D, "vq_encode: identity projection needs C == D (C=%d D=%d)", C, D);
   BC_REQUIRE(bc::aligned16(cb_norm), "vq_encode: codebook must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)s;
-  if (D == SC_D && N >= SC_FRAMES / 2 && bc::aligned16(z)) {
-    // register-tiled scan over shared-memory code tiles (small calls keep the per-warp kernel: more CTAs than SMs there)
-    static bool configured[64] = {false};
-    int dev = 0;
+  if (D == SC_D && N >= 8192 && bc::aligned16(z)) {
+    // register-tiled scan over shared-memory code tiles: 8 frames per thread when that still fills the chip, 2 below
+    // (four times the CTAs at a lower FMA density); tiny calls keep the per-warp kernel (more CTAs than SMs there)
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(vq_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(vq_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    typedef void (*scan_fn)(const float*, const float*, const float*, const float*, int32_t*, float*, float*, int, int, int);
+    const scan_fn k8 = margin ? vq_scan_kernel<true, 8> : vq_scan_kernel<false, 8>;
+    const scan_fn k2 = margin ? vq_scan_kernel<true, 2> : vq_scan_kernel<false, 2>;
+    static bool configured[64][2] = {{false}};
+    if (dev < 0 || dev >= 64 || !configured[dev][margin ? 1 : 0]) {
+      cudaError_t e = cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
       if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(vq_scan)");
-      if (dev >= 0 && dev < 64) configured[dev] = true;
+      if (dev >= 0 && dev < 64) configured[dev][margin ? 1 : 0] = true;
     }
-    const unsigned grid = (unsigned)(((long long)N + SC_FRAMES - 1) / SC_FRAMES);
-    if (margin) vq_scan_kernel<true><<<grid, SC_THREADS, SC_SMEM, st>>>(z, w_in, b_in, cb_norm, idx, margin, z_e, N, C, Kc);
-    else        vq_scan_kernel<false><<<grid, SC_THREADS, SC_SMEM, st>>>(z, w_in, b_in, cb_norm, idx, margin, z_e, N, C, Kc);
-    BC_LAUNCH_CHECK("vq_scan_kernel");
+    // whole waves of 2048-frame CTAs (two per SM) first; what is left -- or an input smaller than one such wave -- goes to
+    // 512-frame CTAs, so that neither a tiny grid nor a nearly empty last wave leaves most of the chip idle
+    const long long wave8 = (long long)SC_THREADS * 8 * 2 * sms;
+    const long long n8 = ((long long)N / wave8) * wave8;
+    if (n8 > 0) {
+      k8<<<(unsigned)(n8 / (SC_THREADS * 8)), SC_THREADS, SC_SMEM, st>>>(z, w_in, b_in, cb_norm, idx, margin, z_e, (int)n8, C, Kc);
+      BC_LAUNCH_CHECK("vq_scan_kernel");
+    }
+    const long long rem = (long long)N - n8;
+    if (rem > 0) {
+      k2<<<(unsigned)((rem + SC_THREADS * 2 - 1) / (SC_THREADS * 2)), SC_THREADS, SC_SMEM, st>>>(
+          z + (size_t)n8 * C, w_in, b_in, cb_norm, idx + n8, margin ? margin + n8 : nullptr, z_e ? z_e + (size_t)n8 * D : nullptr, (int)rem, C, Kc);
+      BC_LAUNCH_CHECK("vq_scan_kernel");
+    }
     return BC_OK;
   }
   const size_t smem = w_in ? (size_t)D * C * sizeof(float) : 0;

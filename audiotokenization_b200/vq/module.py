@@ -21,9 +21,15 @@ from .. import ops
 from . import activations
 from .alias_free_torch import Activation1d
 
+def _os_env_flag(name: str, default: bool) -> bool:
+    import os
+    v = os.environ.get(name)
+    return default if v is None else v not in ("0", "false", "False", "")
+
+
 _PRECISION = ["fp32"]
 LSTM_TENSOR_CORE = [True]   # tensor-core modes: run the LSTM recurrence on tcgen05 when H allows
-LSTM_WAVEFRONT = [True]     # ... and, for batches whose two layers fit the chip side by side, as a two-layer wave front
+LSTM_WAVEFRONT = [_os_env_flag("BC_LSTM_WAVEFRONT", True)]     # ... and, for batches whose two layers fit the chip side by side, as a two-layer wave front
 LSTM_WAVEFRONT_CHUNK = [128]   # steps per chunk of the wave front
 
 

@@ -88,8 +88,10 @@ def traffic(path, out_json, precision):
     agg = {}
     for r in rd:
         name = r["Kernel Name"]
-        fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel", "conv1d_f32_kernel", "lstm_tc_kernel",
-                                "stem_conv_kernel", "vq_encode_kernel") if f in name), None)
+        name = name.replace("conv_stream_pair_kernel", "conv_stream_kernel")   # one family, two forms (bench.py's label)
+        fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel",
+                                "conv1d_f32_kernel", "lstm_tc_kernel", "stem_conv", "tail_conv", "vq_scan_kernel", "vq_encode_kernel", "snake_aa2_kernel",
+                                "snake_kernel") if f in name), None)
         if fam is None:
             continue
         v = float(r["Metric Value"].replace(",", ""))
@@ -113,7 +115,8 @@ def traffic(path, out_json, precision):
         cur = json.load(open(out_json))
     cur[precision] = res
     cur["_how"] = ("ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over "
-                   "`bench.py --clips-per-gpu 8 --steps 1` (micro-batch 8: the launch shapes of the full bench's conv kernels)")
+                   "`BC_LSTM_WAVEFRONT=0 bench.py --clips-per-gpu 8 --steps 1` (micro-batch 8: the launch shapes of the full bench's conv kernels; "
+                   "the small-batch LSTM wave front is switched off so that the LSTM and its input projection are single launches as in the full bench)")
     json.dump(cur, open(out_json, "w"), indent=1, sort_keys=True)
     print(json.dumps(res, indent=1))
 
