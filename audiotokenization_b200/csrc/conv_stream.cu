@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <cuda.h>      // CUtensorMap + enums only; the encoder comes from cudaGetDriverEntryPoint (no libcuda link)
 
 namespace {
 using namespace bc::tc;
@@ -95,7 +96,16 @@ constexpr int MAX_TPU = 8;             // taps per weight unit (issue block is u
 constexpr uint32_t UNIT_MAX_BYTES = 32768;
 
 enum { B_A_FULL = 0, B_A_EMPTY = 4, B_B_FULL = 8, B_B_EMPTY = 16, B_ACC1_FULL = 24, B_ACC1_EMPTY = 26,
-       B_A2_FULL = 28, B_A2_EMPTY = 30, B_ACC2_FULL = 32, B_ACC2_EMPTY = 34, B_B_READY = 36, N_BARS = 44 };
+       B_A2_FULL = 28, B_A2_EMPTY = 30, B_ACC2_FULL = 32, B_ACC2_EMPTY = 34, B_B_READY = 36, B_X_FULL = 44, B_X_EMPTY = 52,
+       N_BARS = 60 };
+constexpr int MAX_NX = 8;
+#ifndef BC_STREAM_XGPB
+#define BC_STREAM_XGPB 2
+#endif
+#ifndef BC_STREAM_XWANT      // bytes of x the ring should hold in flight
+#define BC_STREAM_XWANT 49152u
+#endif
+constexpr uint32_t XT_STAGE_BYTES = 8192;   // TMA form: two swizzled [32 rows][128 B] store tiles per store warp
 
 struct SParams {
   const float* x;
@@ -114,7 +124,9 @@ struct SParams {
   int N, groups, tpu, upg, gpu1;
   int slab_rows, rpp, NA, NB, acc_stages, acc_stride, epi_warps;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
-  int tiles_per_item, tiles_per_nt, total_tiles;
+  int NX, x_rows, x_nbox, x_gpb;   // TMA form: ring of NX fp32 units [x_rows][16 * x_gpb channels], x_nbox units per (tile, x_gpb groups)
+  uint32_t x_unit, x_bytes;        // unit stride in the ring / bytes one box delivers
+  int tiles_per_item, tiles_per_nt, total_tiles, n_tiles;
   int pairs_per_nt, total_pairs;   // pair form: tile pairs (2q, 2q+1) inside one n-tile; an odd count leaves rank 1 a phantom tile
   uint32_t idesc;
   int tmem_cols;
@@ -151,28 +163,32 @@ __device__ __forceinline__ void store_quad(const float4& v, uint8_t* d8, uint32_
   }
 }
 
-// (n-tile, item, tile-in-item) of a CTA's current tile, advanced incrementally: the tile loop has no division
+// (n-tile, item, tile-in-item) of a CTA's current tile, advanced incrementally: the tile loop has no division.
+// Tile order: the n-tiles of one 128-step row tile are NEIGHBOURS (tile = row_tile * n_tiles + nt), so the CTAs that run
+// side by side read the same x tile and it comes from HBM once (n-tile-major order streamed x once per n-tile: 16 times
+// for the 512 -> 2048 LSTM input projection, which made that launch HBM-bound).
 struct TilePos {
-  int nt, b, tt;
-  __device__ __forceinline__ void init(int tile, int tiles_per_item, int B) {
-    const int per_nt = tiles_per_item * B;
-    nt = tile / per_nt;
-    const int rem = tile - nt * per_nt;
-    b = rem / tiles_per_item;
-    tt = rem - b * tiles_per_item;
+  int nt, b, tt, inc_nt, inc_rt;
+  __device__ __forceinline__ void init(int tile, int inc, int tiles_per_item, int n_tiles) {
+    const int rt = tile / n_tiles;
+    nt = tile - rt * n_tiles;
+    b = rt / tiles_per_item;
+    tt = rt - b * tiles_per_item;
+    inc_rt = inc / n_tiles;
+    inc_nt = inc - inc_rt * n_tiles;
   }
-  __device__ __forceinline__ void advance(int inc, int tiles_per_item, int B) {
-    tt += inc;
-    while (tt >= tiles_per_item) {
-      tt -= tiles_per_item;
-      if (++b == B) { b = 0; ++nt; }
-    }
+  __device__ __forceinline__ void advance(int tiles_per_item, int n_tiles) {
+    nt += inc_nt;
+    tt += inc_rt;
+    if (nt >= n_tiles) { nt -= n_tiles; ++tt; }
+    while (tt >= tiles_per_item) { tt -= tiles_per_item; ++b; }
   }
 };
 
 // The tiles one CTA walks, in order.  Single-CTA form: tiles first, first + step, ... (TilePos, no division per tile).
-// Pair form: the cluster takes the tile PAIRS pi, pi + npairs, ...; pair Q covers tiles 2q + {0, 1} of n-tile nt = Q / ppn
-// and this CTA the one of its rank (`valid` false: the phantom tile behind an odd count -- staged as zeros, never stored).
+// Pair form: the cluster takes the tile PAIRS Q = pi, pi + npairs, ...; pair Q covers row tiles 2q + {0, 1} (q = Q / n_tiles)
+// of n-tile Q % n_tiles, and this CTA the one of its rank (`valid` false: the phantom tile behind an odd count -- staged
+// as zeros, never stored).
 template <bool PAIR>
 struct Walk {
   int nt, b, tt;
@@ -180,20 +196,21 @@ struct Walk {
   TilePos tp;
   int Q;
   __device__ __forceinline__ void locate(const SParams& p, int rank) {
-    nt = Q / p.pairs_per_nt;
-    const int ti = 2 * (Q - nt * p.pairs_per_nt) + rank;
+    const int q = Q / p.n_tiles;
+    nt = Q - q * p.n_tiles;
+    const int ti = 2 * q + rank;
     valid = ti < p.tiles_per_nt;
     const int tl = valid ? ti : p.tiles_per_nt - 1;
     b = tl / p.tiles_per_item;
     tt = tl - b * p.tiles_per_item;
   }
-  __device__ __forceinline__ void init(const SParams& p, int first, int rank) {
+  __device__ __forceinline__ void init(const SParams& p, int first, int step, int rank) {
     if (PAIR) { Q = first; locate(p, rank); }
-    else { tp.init(first, p.tiles_per_item, p.B); nt = tp.nt; b = tp.b; tt = tp.tt; valid = true; }
+    else { tp.init(first, step, p.tiles_per_item, p.n_tiles); nt = tp.nt; b = tp.b; tt = tp.tt; valid = true; }
   }
   __device__ __forceinline__ void advance(const SParams& p, int step, int rank) {
     if (PAIR) { Q += step; locate(p, rank); }
-    else { tp.advance(step, p.tiles_per_item, p.B); nt = tp.nt; b = tp.b; tt = tp.tt; }
+    else { tp.advance(p.tiles_per_item, p.n_tiles); nt = tp.nt; b = tp.b; tt = tp.tt; }
   }
 };
 
@@ -206,9 +223,21 @@ struct Walk {
 #define STRACE_ON false
 #endif
 
-template <int SPLIT, bool FUSE, bool PAIR>
-__device__ __forceinline__ void conv_stream_body(const SParams& p) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+// Tensor-map TMA forms of the plain convs (XMODE 1, the default: BC_STREAM_TMA): the store warps write swizzled
+// [32 rows][128 B] tiles that leave by cp.async.bulk.tensor stores (UTMASTG) instead of a transposing pass through a padded
+// staging block + coalesced STG -- the STORE stage of a tile falls from 4.0 k to 1.9 k cycles and the output-heavy LSTM
+// input projection (512 -> 2048, 10 GB of y per launch) runs 16 % faster; the other convs are within +-2 %.
+// XMODE 2 (BC_STREAM_TMA=2) also moves x by TMA: a loader thread keeps a ring of fp32 boxes {16 channels, x_rows rows} in
+// flight (UTMALDG -> X_FULL) and the producers read them from shared memory.  Measured NOT faster (32->64: 266 us both
+// ways, 64->128 / 128->256 / 256->512 4-30 % slower): the producers are not waiting for HBM, they are bound by their own
+// arithmetic (SnakeBeta with range reduction + the hi/lo split: ~45 instructions per 4 elements, one dependent chain per
+// float4), and the extra shared-memory round trip of x costs more than the shorter load latency gains.
+// XMODE: 0 = no tensor maps, 1 = y by TMA stores (x through the producers' own loads), 2 = x and y by TMA.
+template <int SPLIT, bool FUSE, bool PAIR, int XMODE = 0>
+__device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtensorMap* tmx = nullptr, const CUtensorMap* tmy = nullptr) {
+  constexpr bool XT = XMODE != 0, XL = XMODE == 2;
+  static_assert(!(XT && FUSE), "the TMA form exists for the plain convs");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = PAIR ? (int)cluster_rank() : 0;
   // hand-offs towards the MMA thread come from both CTAs of a pair and land on the leader's barrier; hand-offs from it
@@ -223,11 +252,14 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
   const uint32_t a_split = 2u * plane_bytes;
   const uint32_t a2_split = (uint32_t)(A2_CH / 8) * A2_PLANE;
   const uint32_t a2_chunk = a2_split * SPLIT;
-  uint8_t* sA = smem_raw;
+  // TMA form: the swizzled store tiles come first (1024-byte aligned), the x ring sits behind the weight ring
+  uint8_t* sA = smem_raw + (XT ? (size_t)p.epi_warps * XT_STAGE_BYTES : 0);
   uint8_t* sB = sA + (size_t)p.a_stage * p.NA;
   uint8_t* sA2 = sB + (size_t)p.unit_bytes * p.NB;
-  uint8_t* sStage = sA2 + (FUSE ? 2u * a2_chunk : 0u);   // EPI_WARPS x [32][EPI_LD] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + p.epi_warps * 32 * EPI_LD * 4);
+  uint8_t* sX = sA2;                                       // XT: NX x x_unit
+  uint8_t* sStage = XT ? smem_raw : sA2 + (FUSE ? 2u * a2_chunk : 0u);   // EPI_WARPS x [32][EPI_LD] fp32
+  uint64_t* bars = XT ? reinterpret_cast<uint64_t*>(sX + (size_t)p.NX * p.x_unit)
+                      : reinterpret_cast<uint64_t*>(sStage + p.epi_warps * 32 * EPI_LD * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
   uint32_t* s_off = tmem_slot + 2;   // [32 + MAX_TPU] slab-row shift of tap k (16-byte units), padded for the unrolled issue block
   float* sPar = reinterpret_cast<float*>(s_off + 32 + MAX_TPU + 2);   // fused: b7 | snake2 a | snake2 1/b | b1, N floats each (16-byte aligned)
@@ -245,6 +277,12 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
       mbar_init(BAR(B_B_EMPTY + s), 1);
       mbar_init(BAR(B_B_READY + s), 2);
     }
+    if (XL) {
+      for (int s = 0; s < MAX_NX; ++s) {
+        mbar_init(BAR(B_X_FULL + s), 1);
+        mbar_init(BAR(B_X_EMPTY + s), p.x_gpb * (N_PROD / p.NA));
+      }
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(B_ACC1_FULL + s), 1);
       mbar_init(BAR(B_ACC1_EMPTY + s), NCTA * (FUSE ? MID_WARPS : p.epi_warps));
@@ -260,6 +298,12 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
     s_off[tid] = (uint32_t)(sh % p.stride) * (uint32_t)p.rpp + (uint32_t)(sh / p.stride);
   }
   if (tid == 0) { s_off[32 + MAX_TPU] = p.idesc; s_off[32 + MAX_TPU + 1] = (uint32_t)p.dil; }
+  if (XL && (p.flags & BC_CONV_SNAKE_IN)) {   // SnakeBeta parameters of the prologue: a | 1/b, C_in floats each
+    for (int i = tid; i < p.C_in; i += S_THREADS) {
+      sPar[i] = __ldg(p.sa1 + i);
+      sPar[p.C_in + i] = __ldg(p.sib1 + i);
+    }
+  }
   if (FUSE) {
     for (int i = tid; i < p.N; i += S_THREADS) {
       sPar[i] = __ldg(p.bias + i);
@@ -311,18 +355,80 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
     const int rr_step = rstep / p.stride, ph_step = rstep - rr_step * p.stride;
     const uint32_t dst_off = (uint32_t)(c4 >> 1) * plane_bytes + (uint32_t)(c4 & 1) * 8u;
     int slot_c = 0, use_c = 0, sq = 0;   // running ring position over ALL stages (every team counts every stage)
+    uint32_t xslot = 0, xph = 0;         // TMA form: ring position of the next x unit (same count in every team)
     Walk<PAIR> tp;
-    tp.init(p, first, rank);
+    tp.init(p, first, step, rank);
     for (int it = 0; it < n_my; ++it, tp.advance(p, step, rank)) {
       const int b = tp.b;
       const int t0 = tp.tt * BM;
       // a phantom tile (pair form, odd tile count) is staged as if it lay entirely beyond the item: all zeros
       const int g0row = tp.valid ? t0 * p.stride - p.pad_left + (tp.nt >= p.nt_shift ? 1 : 0) : p.T_in + p.slab_rows;
       const float* xb = p.x + (size_t)b * p.T_in * p.C_in + c4 * 4;
-      long long wE = 0;
+      long long wE = 0, wL = 0, wM = 0, wS = 0;
       for (int g = 0; g < p.groups; ++g, ++sq) {
         const int slot = slot_c, use = use_c;
         if (++slot_c == p.NA) { slot_c = 0; ++use_c; }
+        if (XL) {
+          const int gsub = g % p.x_gpb;             // a unit carries x_gpb neighbouring groups (one team each)
+          const bool last_sub = gsub == p.x_gpb - 1;
+          if (slot != team) {           // another team's group: only the ring position moves on
+            if (last_sub) {
+              xslot += (uint32_t)p.x_nbox;
+              while (xslot >= (uint32_t)p.NX) { xslot -= (uint32_t)p.NX; xph ^= 1u; }
+            }
+            continue;
+          }
+          if (g == 0 && tw == 0) STRACE(0);
+          float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+          if (snake) {
+            sa = *reinterpret_cast<const float4*>(sPar + g * 16 + c4 * 4);
+            sb = *reinterpret_cast<const float4*>(sPar + p.C_in + g * 16 + c4 * 4);
+          }
+          uint8_t* dst = sA + (size_t)slot * p.a_stage + dst_off;
+          const uint32_t xpitch = (uint32_t)p.x_gpb * 64u;
+          uint32_t us = xslot, uph = xph;           // this group's units
+          for (int c = 0; c < p.x_nbox; ++c) {
+            long long tx_ = STRACE_ON ? clock64() : 0;
+            mbar_wait(BAR(B_X_FULL + us), uph);
+            if (STRACE_ON) wL += clock64() - tx_;
+            if (c == 0) {
+              long long tw_ = STRACE_ON ? clock64() : 0;
+              mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
+              if (STRACE_ON) wE += clock64() - tw_;
+            }
+            const uint8_t* src = sX + (size_t)us * p.x_unit + (size_t)gsub * 64 + (size_t)c4 * 16;
+            // slab row r = c * x_rows + i lives at (phase r % stride, row r / stride)
+            int ph = 0, rr = r_first;
+            if (p.stride > 1) { const int r = c * p.x_rows + r_first; rr = r / p.stride; ph = r - rr * p.stride; }
+            for (int i0 = r_first; i0 < p.x_rows; i0 += rstep * P_BATCH) {
+              float4 v4[P_BATCH];
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j)
+                if (i0 + rstep * j < p.x_rows) v4[j] = *reinterpret_cast<const float4*>(src + (size_t)(i0 + rstep * j) * xpitch);
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) {
+                if (i0 + rstep * j < p.x_rows) {
+                  float4 v = v4[j];
+                  if (snake) snake4<SPLIT>(v, sa, sb);   // snake(0) == 0: rows outside the item stay zero
+                  store_quad<SPLIT>(v, dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u, a_split);
+                }
+                ph += ph_step; rr += rr_step;
+                if (ph >= p.stride) { ph -= p.stride; ++rr; }
+              }
+            }
+            if (STRACE_ON) wM += clock64() - tx_;
+            __syncwarp();
+            if (STRACE_ON) wS += clock64() - tx_;
+            if (lane == 0) mbar_arrive(BAR(B_X_EMPTY + us));        // this warp has read its rows of the unit
+            if (++us == (uint32_t)p.NX) { us = 0; uph ^= 1u; }
+          }
+          if (last_sub) { xslot = us; xph = uph; }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) ARRIVE_MMA(BAR(B_A_FULL + slot));
+          if (g == p.groups - 1 && tw == 0) STRACE(1);
+          continue;
+        }
         if (slot != team) continue;
         if (g == 0 && tw == 0) STRACE(0);
         float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
@@ -381,6 +487,17 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
               if (STRACE_ON) wE += clock64() - tw_;
               waited = true;
             }
+            long long tl_ = 0;
+            if (STRACE_ON) {   // debug: time until the batch's loads have all landed, then the math + stores
+              tl_ = clock64();
+              float acc_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) acc_ += v4[j].x;
+              if (acc_ == 1.2345e-30f) ++wE;
+              const long long t2_ = clock64();
+              wL += t2_ - tl_;
+              tl_ = t2_;
+            }
 #pragma unroll
             for (int j = 0; j < P_BATCH; ++j) {
               if (r0 + rstep * j < p.slab_rows) {
@@ -393,6 +510,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
               ph += ph_step; rr += rr_step;
               if (ph >= p.stride) { ph -= p.stride; ++rr; }
             }
+            if (STRACE_ON) wM += clock64() - tl_;
           }
         }
         if (!waited) mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
@@ -401,7 +519,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
         if (lane == 0) ARRIVE_MMA(BAR(B_A_FULL + slot));
         if (g == p.groups - 1 && tw == 0) STRACE(1);
       }
-      if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) p.trace[it * 16 + 12] = wE;
+      if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) { p.trace[it * 16 + 12] = wE; p.trace[it * 16 + 13] = wL; p.trace[it * 16 + 14] = wM; p.trace[it * 16 + 15] = wS; }
     }
   } else if (warp >= LOAD_WARP) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_CTRL));
@@ -410,7 +528,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
     if (lane == 0 && !freerun && !free_b) {
       uint32_t slot = 0, phase = 1;   // ring position; `phase` = parity a free slot's empty barrier must have completed
       Walk<PAIR> ltp;
-      ltp.init(p, first, rank);
+      ltp.init(p, first, step, rank);
       const uint32_t uB = smem_u32(sB);
       const int nchunk = p.N / A2_CH;
       const int last = defer ? n_my : n_my - 1;
@@ -457,6 +575,25 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
         mbar_wait(BAR(B_B_FULL + slot), phase);
         mbar_arrive_leader(BAR(B_B_READY + slot));
         if (++slot == (uint32_t)p.NB) { slot = 0; phase ^= 1u; }
+      }
+    }
+   } else if (XL && warp == LOAD_WARP + 3) {
+    // ======================= X LOADER (TMA form): fp32 boxes of x, in the order the producer teams consume them =======================
+    if (lane == 0 && !freerun) {
+      tma_prefetch_desc(tmx);
+      Walk<PAIR> xtp;
+      xtp.init(p, first, step, rank);
+      const uint32_t uX = smem_u32(sX);
+      uint32_t slot = 0, phase = 1;
+      for (int it = 0; it < n_my; ++it, xtp.advance(p, step, rank)) {
+        // a phantom tile (pair form, odd tile count) is read from beyond the item: all zeros
+        const int g0row = xtp.valid ? xtp.tt * BM * p.stride - p.pad_left + (xtp.nt >= p.nt_shift ? 1 : 0) : p.T_in + p.slab_rows;
+        for (int g = 0; g < p.groups; g += p.x_gpb)
+          for (int c = 0; c < p.x_nbox; ++c) {
+            mbar_wait(BAR(B_X_EMPTY + slot), phase);
+            tma_load_3d(uX + slot * p.x_unit, tmx, g * 16, g0row + c * p.x_rows, xtp.b, BAR(B_X_FULL + slot), p.x_bytes);
+            if (++slot == (uint32_t)p.NX) { slot = 0; phase ^= 1u; }
+          }
       }
     }
    } else if (warp == MMA_WARP && (!PAIR || rank == 0)) {
@@ -675,11 +812,56 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
     float* sT = reinterpret_cast<float*>(sStage) + (size_t)ew * (32 * EPI_LD);
     const int crow = lane >> 3, cchunk = (lane & 7) * 4;          // coalesced mapping: rows crow + 4*i, 4 floats at cchunk
     Walk<PAIR> tp;
-    tp.init(p, first, rank);
+    tp.init(p, first, step, rank);
+    int xt_seq = 0;      // TMA form: store tiles written so far by this warp
     for (int it = 0; it < n_my; ++it, tp.advance(p, step, rank)) {
       const int as = p.acc_stages == 2 ? (it & 1) : 0, ause = p.acc_stages == 2 ? (it >> 1) : it;
       const int nt = tp.nt, b = tp.b;
       const int trow0 = tp.tt * BM + q * 32;     // first output row of this warp's block
+      if (XT) {
+        // TMA form: the lane's accumulator row goes into a [32 rows][128 B] tile with the 128-byte swizzle (16-byte chunk
+        // index ^ row % 8: conflict-free although every lane writes its own row), which one TMA store un-swizzles on its
+        // way to y; rows beyond T_out are clipped by the tensor map.  Two tiles per warp: the previous block's store
+        // reads its tile while this block is written.
+        const uint32_t fullbar = BAR(B_ACC1_FULL + as), emptybar = BAR(B_ACC1_EMPTY + as);
+        const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+        const float* bp = bias ? bias + (size_t)nt * p.N : nullptr;
+        for (int c0 = cb0; c0 < p.N; c0 += cbstep, ++xt_seq) {
+          if (c0 == cb0) {
+            mbar_wait(fullbar, (uint32_t)(ause & 1));
+            tc_fence_after();
+            if (warp == EPI_WARP0) STRACE(8);
+          }
+          uint32_t r[32];
+          tmem_load32(taddr + (uint32_t)c0, r);
+          if (c0 + cbstep >= p.N) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ARRIVE_MMA(emptybar);
+          }
+          if (xt_seq >= 2) {                     // the store that read this tile two blocks ago is done with it
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+          uint8_t* tile = sStage + (size_t)ew * XT_STAGE_BYTES + (size_t)(xt_seq & 1) * 4096;
+          const uint32_t own = smem_u32(tile) + (uint32_t)lane * 128u, sw = ((uint32_t)lane & 7u) << 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                   __uint_as_float(r[4 * j + 3]));
+            if (bp) v = add4(v, __ldg(reinterpret_cast<const float4*>(bp + c0) + j));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(own + (((uint32_t)j << 4) ^ sw)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (tp.valid && !DBG_SKIP(4)) tma_store_3d(tmy, nt * p.N + c0, trow0, b, smem_u32(tile));
+            bulk_commit_group();
+          }
+        }
+        if (warp == EPI_WARP0) STRACE(9);
+        continue;
+      }
       const size_t off0 = ((size_t)b * p.T_out + trow0 + crow) * p.C_out + (size_t)nt * p.N + cchunk;
       const float* rp = (p.res && !DBG_SKIP(4)) ? p.res + off0 : nullptr;
       float* yp = p.y + off0;
@@ -749,6 +931,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p) {
       }
       if (warp == EPI_WARP0) STRACE(9);
     }
+    if (XT && lane == 0) bulk_wait_all();      // the last stores have left shared memory and are visible
   }
 done:
 #undef BAR
@@ -775,15 +958,167 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Roles<FUSE>::THREADS
   conv_stream_body<SPLIT, FUSE, true>(p);
 }
 
+// TMA form of the plain conv (tensor maps of x and y as grid constants)
+template <int SPLIT, int XMODE>
+__global__ void __launch_bounds__(Roles<false>::THREADS, 1)
+conv_stream_tma_kernel(const SParams p, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  conv_stream_body<SPLIT, false, false, XMODE>(p, &tmx, &tmy);
+}
+template <int SPLIT, int XMODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Roles<false>::THREADS, 1)
+conv_stream_tma_pair_kernel(const SParams p, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  conv_stream_body<SPLIT, false, true, XMODE>(p, &tmx, &tmy);
+}
+
 long long* g_stream_trace = nullptr;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// fp32 channels-last tensor [B][T][C] as a 3-D map {C, T, B} with box {box_c, box_t, 1}
+int encode_cl_map(CUtensorMap* m, const float* base, int B, int T, int C, int box_c, int box_t, bool swizzle128) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return bc::fail(BC_ENODEVICE, "conv(stream): cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 4u, (cuuint64_t)T * (cuuint64_t)C * 4u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_t, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return bc::fail(BC_EINVAL, "conv(stream): cuTensorMapEncodeTiled failed (%d) for [%d][%d][%d] box %d x %d", (int)r, B, T, C, box_c, box_t);
+  return BC_OK;
+}
 
 struct StreamPlan {
   int N, n_tiles, groups, tpu, upg, gpu1, slab_rows, rpp, NA, NB, acc_stages, acc_stride, tmem_cols, split, epi_warps;
-  uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
+  int NX, x_rows, x_nbox, x_gpb;
+  uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes, x_unit, x_bytes;
   size_t smem;
 };
 
-bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused, StreamPlan* pl, bool pair = false) {
+// Shared-memory plan of the TMA form (N, split, tap_bytes already set): 8 KB swizzled store tiles per store warp, TWO
+// activation stages (the x ring, not the stage count, now covers the HBM latency), a weight ring of >= 3 units and an x
+// ring that holds about 48 KB of fp32 boxes in flight.
+bool stream_plan_tma(int C_in, int K, int stride, int dilation, StreamPlan* pl, bool loads) {
+  const int N = pl->N, split = pl->split;
+  pl->slab_rows = (BM - 1) * stride + (K - 1) * dilation + 1;
+  pl->rpp = (pl->slab_rows + stride - 1) / stride;
+  pl->x_rows = stride > 1 ? pl->rpp : pl->slab_rows;       // one box per phase-sized run of slab rows
+  pl->x_nbox = stride > 1 ? stride : 1;
+  if (pl->x_rows > 256) return false;                      // TMA box limit
+  // a box carries BC_STREAM_XGPB (2) neighbouring 16-channel groups: TMA's cost is per box ROW, and 64-byte rows only
+  // reached ~7 B/clk per SM
+  pl->x_gpb = BC_STREAM_XGPB;
+  while ((C_in / 16) % pl->x_gpb != 0) pl->x_gpb >>= 1;
+  pl->x_bytes = (uint32_t)pl->x_rows * 64u * (uint32_t)pl->x_gpb;
+  pl->x_unit = (pl->x_bytes + 127u) & ~127u;
+  pl->plane_bytes = (uint32_t)stride * pl->rpp * 16u;
+  while (pl->plane_bytes % 128u != 64u) pl->plane_bytes += 16u;
+  pl->a_stage = (uint32_t)((size_t)split * 2 * pl->plane_bytes + 127) & ~127u;
+  if ((size_t)pl->plane_bytes * 2 >= (1u << 18)) return false;
+  pl->epi_warps = 4;
+  const size_t misc = N_BARS * 8 + 64 + (32 + MAX_TPU + 2) * 4 + 16 + (size_t)pl->epi_warps * XT_STAGE_BYTES + (size_t)2 * C_in * 4;
+  const size_t budget = 225 * 1024;
+  int want = (int)((BC_STREAM_XWANT + pl->x_unit - 1) / pl->x_unit);
+  if (want > MAX_NX) want = MAX_NX;
+  if (want < 2) want = 2;
+  if (!loads) {
+    // stores by TMA, x through the producers' own loads: the old ring logic with the larger store tiles
+    pl->NX = 0; pl->x_unit = 0; pl->x_bytes = 0; pl->x_gpb = 1;
+    int tpu = (int)(UNIT_MAX_BYTES / pl->tap_bytes);
+    if (tpu < 1) tpu = 1;
+    if (tpu > MAX_TPU) tpu = MAX_TPU;
+    if (tpu > K) tpu = K;
+    pl->upg = (K + tpu - 1) / tpu;
+    tpu = (K + pl->upg - 1) / pl->upg;
+    pl->tpu = tpu;
+    pl->unit_bytes = (uint32_t)tpu * pl->tap_bytes;
+    int gpu1 = 1;
+    while (gpu1 * 2 <= tpu && gpu1 * 2 <= 4) gpu1 *= 2;
+    pl->gpu1 = gpu1;
+    int NB = (int)(98304u / pl->unit_bytes), NA = 0;
+    if (NB > 8) NB = 8;
+    if (NB < 3) NB = 3;
+    const int groups = C_in / 16;
+    const int want_na = groups < 4 ? (groups < 2 ? 2 : groups) : 4;
+    int best_nb = 0, best_na = 0;
+    for (; NB >= 3; --NB) {
+      const size_t used = (size_t)NB * pl->unit_bytes + misc;
+      if (used >= budget) continue;
+      NA = (int)((budget - used) / pl->a_stage);
+      if (NA > 4) NA = 4;
+      if (NA > best_na) { best_na = NA; best_nb = NB; }
+      if (NA >= want_na) break;
+    }
+    if (best_na < 2) return false;
+    NA = best_na;
+    while (Roles<false>::PROD % NA != 0) --NA;
+    pl->NA = NA; pl->NB = best_nb;
+    pl->acc_stride = N;
+    pl->acc_stages = 2 * N <= 512 ? 2 : 1;
+    int cols = pl->acc_stages * pl->acc_stride, pw = 32;
+    while (pw < cols) pw <<= 1;
+    pl->tmem_cols = pw;
+    pl->smem = (size_t)best_nb * pl->unit_bytes + misc + (size_t)NA * pl->a_stage;
+    return true;
+  }
+  int best_nx = 0;
+  for (uint32_t cap = UNIT_MAX_BYTES; cap >= 16384u && best_nx < want; cap >>= 1) {
+    int tpu = (int)(cap / pl->tap_bytes);
+    if (tpu < 1) tpu = 1;
+    if (tpu > MAX_TPU) tpu = MAX_TPU;
+    if (tpu > K) tpu = K;
+    const int upg = (K + tpu - 1) / tpu;
+    tpu = (K + upg - 1) / upg;
+    const uint32_t unit_bytes = (uint32_t)tpu * pl->tap_bytes;
+    int NB = (int)(98304u / unit_bytes);
+    if (NB > 8) NB = 8;
+    for (; NB >= 3; --NB) {
+      const size_t used = (size_t)NB * unit_bytes + misc + 2 * (size_t)pl->a_stage;
+      if (used >= budget) continue;
+      int nx = (int)((budget - used) / pl->x_unit);
+      if (nx > MAX_NX) nx = MAX_NX;
+      if (nx > best_nx) {
+        best_nx = nx;
+        pl->tpu = tpu; pl->upg = upg; pl->unit_bytes = unit_bytes; pl->NB = NB; pl->NX = nx;
+      }
+      if (best_nx >= want) break;
+    }
+  }
+  if (best_nx < 2) return false;
+  int gpu1 = 1;
+  while (gpu1 * 2 <= pl->tpu && gpu1 * 2 <= 4) gpu1 *= 2;
+  pl->gpu1 = gpu1;
+  // what is left goes to more activation stages (= producer teams), up to four
+  const size_t used = (size_t)pl->NB * pl->unit_bytes + misc + (size_t)pl->NX * pl->x_unit;
+  int NA = (int)((budget - used) / pl->a_stage);
+  const int groups = C_in / 16;
+  if (NA > 4) NA = 4;
+  if (NA > groups) NA = groups < 2 ? 2 : groups;
+  while (Roles<false>::PROD % NA != 0) --NA;             // teams of Roles<false>::PROD / NA warps
+  if (NA < 2) return false;
+  pl->NA = NA;
+  pl->acc_stride = N;
+  pl->acc_stages = 2 * N <= 512 ? 2 : 1;
+  int cols = pl->acc_stages * pl->acc_stride, pw = 32;
+  while (pw < cols) pw <<= 1;
+  pl->tmem_cols = pw;
+  pl->smem = used + (size_t)NA * pl->a_stage;
+  return true;
+}
+
+bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int precision, int fused, StreamPlan* pl, bool pair = false, bool tma = false) {
   if (precision != BC_PREC_BF16 && precision != BC_PREC_BF16X3) return false;
   if (C_in % 16 != 0 || C_in < 32 || K < 1 || K > 32 || stride < 1 || dilation < 1) return false;
   if (stride > 1 && dilation > 1) return false;
@@ -800,6 +1135,8 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   pl->n_tiles = C_out / N;
   pl->groups = C_in / 16;
   pl->tap_bytes = (uint32_t)(pair ? N / 2 : N) * 32u * split;   // pair form: every SM holds half of the B rows
+  pl->NX = 0; pl->x_rows = 0; pl->x_nbox = 0; pl->x_gpb = 1; pl->x_unit = 0; pl->x_bytes = 0;
+  if (tma) return !fused && stream_plan_tma(C_in, K, stride, dilation, pl, bc::policy().stream_tma >= 2);
   int tpu = (int)(UNIT_MAX_BYTES / pl->tap_bytes);
   if (tpu < 1) tpu = 1;
   if (tpu > MAX_TPU) tpu = MAX_TPU;
@@ -858,16 +1195,18 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   return true;
 }
 
-int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, bool pair = false) {
+int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, bool pair = false, bool tma = false) {
   p.N = pl.N; p.groups = pl.groups; p.tpu = pl.tpu; p.upg = pl.upg; p.gpu1 = pl.gpu1;
   p.slab_rows = pl.slab_rows; p.rpp = pl.rpp; p.NA = pl.NA; p.NB = pl.NB;
   p.acc_stages = pl.acc_stages; p.acc_stride = pl.acc_stride; p.epi_warps = pl.epi_warps; p.a_stage = pl.a_stage; p.unit_bytes = pl.unit_bytes;
   p.tap_bytes = pl.tap_bytes; p.tmem_cols = pl.tmem_cols; p.plane_bytes = pl.plane_bytes;
+  p.NX = pl.NX; p.x_rows = pl.x_rows; p.x_nbox = pl.x_nbox; p.x_gpb = pl.x_gpb; p.x_unit = pl.x_unit; p.x_bytes = pl.x_bytes;
   p.tiles_per_item = (p.T_out + BM - 1) / BM;
   const long long per_nt = (long long)p.tiles_per_item * p.B;
   const long long total = per_nt * pl.n_tiles;
   if (total > 2147483647ll) return bc::fail(BC_EINVAL, "conv(stream): too many tiles");
   p.tiles_per_nt = (int)per_nt;
+  p.n_tiles = pl.n_tiles;
   p.total_tiles = (int)total;
   p.pairs_per_nt = (int)((per_nt + 1) / 2);
   p.total_pairs = p.pairs_per_nt * pl.n_tiles;
@@ -890,7 +1229,7 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, 
     if (pl.split == 1 && fused) { kern = conv_stream_pair_kernel<1, true>; slot = 6; }
     if (pl.split == 2 && fused) { kern = conv_stream_pair_kernel<2, true>; slot = 7; }
   }
-  static bool configured[64][8] = {{false}};
+  static bool configured[64][16] = {{false}};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -905,6 +1244,29 @@ int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, 
     grid = 2 * (p.total_pairs < max_pairs ? p.total_pairs : max_pairs);
   } else {
     grid = p.total_tiles < sms ? p.total_tiles : sms;
+  }
+  if (tma) {
+    // x boxes: 16 channels x x_rows rows (dense, 64-byte rows); y tiles: 32 channels x 32 rows with the 128-byte swizzle
+    CUtensorMap tmx, tmy;
+    int rc = encode_cl_map(&tmx, p.x, p.B, p.T_in, p.C_in, 16 * p.x_gpb, p.x_rows > 0 ? p.x_rows : 1, false);
+    if (rc != BC_OK) return rc;
+    rc = encode_cl_map(&tmy, p.y, p.B, p.T_out, p.C_out, 32, 32, true);
+    if (rc != BC_OK) return rc;
+    const bool xl = pl.NX > 0;
+    void (*tk)(const SParams, const CUtensorMap, const CUtensorMap) =
+        xl ? (pair ? (pl.split == 2 ? conv_stream_tma_pair_kernel<2, 2> : conv_stream_tma_pair_kernel<1, 2>)
+                   : (pl.split == 2 ? conv_stream_tma_kernel<2, 2> : conv_stream_tma_kernel<1, 2>))
+           : (pair ? (pl.split == 2 ? conv_stream_tma_pair_kernel<2, 1> : conv_stream_tma_pair_kernel<1, 1>)
+                   : (pl.split == 2 ? conv_stream_tma_kernel<2, 1> : conv_stream_tma_kernel<1, 1>));
+    const int tslot = 8 + (xl ? 4 : 0) + (pair ? 2 : 0) + (pl.split == 2 ? 1 : 0);
+    if (dev < 0 || dev >= 64 || !configured[dev][tslot]) {
+      cudaError_t e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(conv_stream_tma)");
+      if (dev >= 0 && dev < 64) configured[dev][tslot] = true;
+    }
+    tk<<<grid, Roles<false>::THREADS, pl.smem, st>>>(p, tmx, tmy);
+    BC_LAUNCH_CHECK(pair ? "conv_stream_tma_pair_kernel" : "conv_stream_tma_kernel");
+    return BC_OK;
   }
   kern<<<grid, fused ? Roles<true>::THREADS : Roles<false>::THREADS, pl.smem, st>>>(p);
   BC_LAUNCH_CHECK(pair ? "conv_stream_pair_kernel" : "conv_stream_kernel");
@@ -933,7 +1295,10 @@ static int conv1d_stream_impl(const float* x, const void* w_image, const float* 
   BC_REQUIRE(B > 0 && T_in > 0 && T_out > 0, "conv1d(stream): bad shape B=%d T_in=%d T_out=%d", B, T_in, T_out);
   BC_REQUIRE(!(flags & BC_CONV_SNAKE_IN) || (snake_a && snake_ib), "conv1d(stream): BC_CONV_SNAKE_IN needs snake_a and snake_ib");
   StreamPlan pl;
-  if (!stream_plan(C_in, C_out, K, stride, dilation, precision, 0, &pl, pair))
+  // TMA form (x boxes and y tiles by tensor map) unless the epilogue needs what only the store-through-registers form has
+  const bool tma = bc::policy().stream_tma && !res && !(flags & BC_CONV_TANH_OUT) &&
+                   stream_plan(C_in, C_out, K, stride, dilation, precision, 0, &pl, pair, true);
+  if (!tma && !stream_plan(C_in, C_out, K, stride, dilation, precision, 0, &pl, pair))
     return bc::fail(BC_EUNSUPPORTED, "conv1d(stream): unsupported geometry C_in=%d C_out=%d K=%d stride=%d dil=%d", C_in, C_out, K, stride, dilation);
   BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w_image) && bc::aligned16(y) && (!res || bc::aligned16(res)) &&
                  (!bias || bc::aligned16(bias)) && (!snake_a || bc::aligned16(snake_a)) && (!snake_ib || bc::aligned16(snake_ib)),
@@ -943,7 +1308,7 @@ static int conv1d_stream_impl(const float* x, const void* w_image, const float* 
   p.bias = bias; p.bias2 = nullptr; p.sa1 = snake_a; p.sib1 = snake_ib; p.sa2 = nullptr; p.sib2 = nullptr;
   p.B = B; p.T_in = T_in; p.T_out = T_out; p.C_in = C_in; p.C_out = C_out; p.K = K; p.stride = stride; p.dil = dilation;
   p.pad_left = pad_left; p.flags = flags; p.nt_shift = 0x7fffffff;
-  return launch_stream(p, pl, 0, (cudaStream_t)s, pair);
+  return launch_stream(p, pl, 0, (cudaStream_t)s, pair, tma);
 }
 
 // 1 when the CTA-pair form has a plan for this geometry (same n_tile as bc_stream_plan) and the policy enables it
@@ -992,7 +1357,8 @@ static int convtr1d_stream_impl(const float* x, const void* w_image, const float
   BC_REQUIRE(B > 0 && T_in > 0 && stride >= 2 && padding >= 0 && padding < stride, "convtr1d(stream): bad shape B=%d T_in=%d stride=%d padding=%d", B, T_in, stride, padding);
   BC_REQUIRE(!(flags & BC_CONV_SNAKE_IN) || (snake_a && snake_ib), "convtr1d(stream): BC_CONV_SNAKE_IN needs snake_a and snake_ib");
   StreamPlan pl;
-  if (!stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl, pair) || C_out % pl.N != 0)
+  const bool tma = bc::policy().stream_tma && !(flags & BC_CONV_TANH_OUT) && stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl, pair, true);
+  if ((!tma && !stream_plan(C_in, stride * C_out, 2, 1, 1, precision, 0, &pl, pair)) || C_out % pl.N != 0)
     return bc::fail(BC_EUNSUPPORTED, "convtr1d(stream): C_in=%d C_out=%d stride=%d has no single-launch plan", C_in, C_out, stride);
   BC_REQUIRE(bc::aligned16(x) && bc::aligned16(w_image) && bc::aligned16(y) && (!bias_tiled || bc::aligned16(bias_tiled)) &&
                  (!snake_a || bc::aligned16(snake_a)) && (!snake_ib || bc::aligned16(snake_ib)),
@@ -1003,7 +1369,7 @@ static int convtr1d_stream_impl(const float* x, const void* w_image, const float
   p.B = B; p.T_in = T_in; p.T_out = T_in; p.C_in = C_in; p.C_out = stride * C_out; p.K = 2; p.stride = 1; p.dil = 1;
   p.pad_left = 1; p.flags = flags;
   p.nt_shift = (stride - padding) * (C_out / pl.N);          // first n-tile of phase ph = stride - padding, the first with q = 1
-  return launch_stream(p, pl, 0, (cudaStream_t)s, pair);
+  return launch_stream(p, pl, 0, (cudaStream_t)s, pair, tma);
 }
 
 extern "C" int bc_convtr1d_stream_fwd(const float* x, const void* w_image, const float* bias_tiled, const float* snake_a,

@@ -680,3 +680,19 @@ def test_fsq_quantizer_matches_oracle(levels, C, B, T):
     assert torch.equal(back, out)
     with pytest.raises(IndexError):
         q.indices_to_codes(torch.full((1, 4), q.codebook_size, dtype=torch.int32, device=DEV))
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_stream_conv_other_tensor_map_modes(mode):
+    """The plain streamed-weight convs run with TMA stores by default (BC_STREAM_TMA=1).  The policy is read once per
+    process, so the two other forms -- no tensor maps at all (0) and x boxes by TMA as well (2) -- are pinned in a
+    subprocess that re-runs the plain-conv, transposed-conv and guard-band cases under that setting."""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BC_STREAM_TMA=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        os.path.join(repo, "tests", "test_gpu_ops.py"), os.path.join(repo, "tests", "test_gpu_guard_bands.py"),
+                        "-k", "stream_conv_matches or conv_transpose1d_tensor_core or single_launch or res_lstm_tensor_core_input"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=repo)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1000:]
