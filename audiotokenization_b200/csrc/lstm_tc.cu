@@ -61,6 +61,21 @@ struct LstmTcParams {
 #define LTRACE(ev) do { } while (0)
 #endif
 
+// Polling a step counter: BC_LSTM_POLL 0 = ld.acquire.gpu every iteration; 1 = relaxed loads and one fence.acq_rel.gpu once
+// the count is reached.  Measured: 1 is SLOWER (B = 512: 13.0 vs 11.3 us per step, B = 1: 6.5 vs 5.0) -- the fence is a
+// full MEMBAR, while the ~1.6 k cycles a poll takes in the step trace are the L2 round trip under the exchange traffic,
+// which the relaxed load pays as well.
+#ifndef BC_LSTM_POLL
+#define BC_LSTM_POLL 0
+#endif
+#if BC_LSTM_POLL == 0
+#define POLL_LD(seen, ptr) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ptr) : "memory")
+#define POLL_FENCE() do { } while (0)
+#else
+#define POLL_LD(seen, ptr) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ptr) : "memory")
+#define POLL_FENCE() asm volatile("fence.acq_rel.gpu;" ::: "memory")
+#endif
+
 // Gate non-linearities of the tensor-core modes: SFU exp + approximate divide (|error| ~ 2e-7, far below the
 // bf16x3 operand error; the fp32 mode runs lstm.cu with expf / tanhf).  Both saturate correctly for ANY finite
 // input: the cell state is unbounded (c grows by up to 1 per step), so tanh must not produce inf/inf.
@@ -145,9 +160,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
               unsigned int seen;
               unsigned int spins = 0;
               do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + m * CNT_STRIDE + c) : "memory");
+                POLL_LD(seen, p.counters + m * CNT_STRIDE + c);
                 if (++spins > (1u << 26)) __trap();
               } while (seen < target);
+              POLL_FENCE();
               asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of other CTAs -> async-proxy reads
             }
             if (c == 0) LTRACE(0);
@@ -355,11 +371,273 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair form (tcgen05 cta_group::2; split precision, an even number of batch tiles; opt-in: BC_LSTM_PAIR=1).
+// MEASURED: bit-identical to the two-tiles-per-CTA form and NOT faster (B = 512, H = 512: 11.3 vs 10.9-11.2 us per step)
+// although it halves the h traffic -- the step is a chain of L2 round trips (h stores + release 3.5 k cycles, the
+// publish becoming visible to a poll 2.5-3.2 k, ~1.6 k per poll, first 64 KB chunk 2.7 k after the counter), not L2 or
+// shared-memory bandwidth; the ping-pong of two independent tiles per CTA hides more of that chain than the pair saves.  The two CTAs of a cluster own
+// TWO batch tiles (M = 256: one each) and 64 gate columns = 16 hidden units: every SM still holds 96 rows of W_hh (rank 0:
+// the w_hi rows of the 64 columns + the first half of w_hi again, rank 1: the w_lo rows + the second half of w_hi -- the
+// two halves of the B operands  [w_hi | w_lo] (N = 128)  and  w_hi (N = 64)  of a pair MMA) and fetches ONE 256 KB h tile per
+// step, but that tile now meets 64 gate columns instead of 32: 512 rows take 128 CTAs x 256 KB of h through L2 and
+// shared memory per step where the two-tiles-per-CTA form takes twice that.  Same arithmetic per element (the same
+// products accumulated in the same order), same exchange buffer, counters (8 arrivals per 128-channel chunk and step
+// instead of 16) and weight image: the per-rank operand halves are gathered from the [slice][H/16][2][hi 32 | lo 32][8]
+// image by 512-byte bulk copies at launch.  Hand-offs as in conv_stream.cu's pair form: bulk copies complete on a barrier
+// of their own CTA and a relay lane forwards "slot full" to the leader, the leader's MMA lane frees slots and publishes
+// accumulators in both CTAs with multicast commits, the gate warps of both CTAs return the accumulator to the leader.
+constexpr int PNS = 64;     // gate columns of a pair slice (two neighbouring 32-column slices of the weight image)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L_THREADS, 1) lstm_pair_kernel(const LstmTcParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_rank();
+  constexpr int j = 0;   // (LTRACE)
+  (void)j;
+  const int H = p.H;
+  constexpr int U = PNS / 4;                           // hidden units of the pair slice
+  const int nchunks = H / KC;
+  const int S = (int)blockIdx.x >> 1;                  // pair slice: image slices 2S, 2S + 1
+  const int m = 2 * (int)blockIdx.y + rank;            // this CTA's batch tile
+  const uint32_t x_bytes = (uint32_t)PNS * H * 2u;     // region X: 64 B-operand rows per 16-channel group and k-plane
+  const uint32_t y_bytes = x_bytes / 2u;               // region Y: 32 rows
+  const uint32_t w_bytes = x_bytes + y_bytes;
+  const uint32_t chunk_split = (uint32_t)LM * KC * 2u;
+  const uint32_t slot_bytes = chunk_split * 2u;
+  constexpr uint32_t acc_cols = 2u * PNS;
+  uint8_t* sW = smem_raw;
+  uint8_t* sA = sW + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)slot_bytes * p.nslot);
+  // bars: full[nslot] | ready[nslot] | empty[nslot] | acc_full | acc_empty | w_full | w_ready
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_full = bar0, bar_ready = bar0 + 8u * p.nslot, bar_empty = bar0 + 16u * p.nslot, bar_accf = bar0 + 24u * p.nslot,
+                 bar_acce = bar_accf + 8u, bar_w = bar_acce + 8u, bar_wr = bar_w + 8u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.nslot + 4);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.nslot; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_ready + 8u * s, 2);
+      mbar_init(bar_empty + 8u * s, 1);
+    }
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_acce, 2 * GATE_WARPS);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_wr, 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(acc_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // both CTAs: barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 3) {
+    // this rank's halves of the B operands, gathered from the 32-column slices 2S and 2S + 1 of the weight image
+    if (lane == 0) mbar_expect_tx(bar_w, w_bytes);
+    __syncwarp();
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.wimg);
+    const int groups = H / 16;
+    for (int i = lane; i < groups * 2 * 3; i += 32) {
+      const int part = i / (groups * 2), gp = i - part * groups * 2;       // part 0, 1: X from slice 2S + part; 2: Y
+      const int slice = 2 * S + (part < 2 ? part : rank);
+      const size_t src = (((size_t)slice * groups * 2 + gp) * 64 + (part < 2 ? rank * 32 : 0)) * 16;
+      const uint32_t dst = part < 2 ? ((uint32_t)gp * 64u + (uint32_t)part * 32u) * 16u : x_bytes + (uint32_t)gp * 32u * 16u;
+      bulk_g2s_notx(smem_u32(sW) + dst, img + src, 512u, bar_w);
+    }
+  }
+
+  const size_t hx_tile = (size_t)2 * (H / 8) * LM * 8;
+  const size_t hx_parity = hx_tile * p.m_tiles;
+
+  if (warp == 0) {
+    // ======================= TMA producer: this CTA's h tile =======================
+    if (lane == 0) {
+      uint32_t cc = 0;
+      for (int t = 0; t < p.T; ++t) {
+        const __nv_bfloat16* src = p.hx + (size_t)((p.t_base + t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
+        for (int c = 0; c < nchunks; ++c, ++cc) {
+          if (t > 0) {
+            const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
+            unsigned int seen, spins = 0;
+            bool first = true;
+            do {
+              POLL_LD(seen, p.counters + m * CNT_STRIDE + c);
+              if (++spins > (1u << 26)) __trap();
+#ifdef BC_TRACE
+              if (c == 0 && first && seen > target - (unsigned int)(KC / U)) { first = false; LTRACE(7); }
+#endif
+            } while (seen < target);
+            (void)first;
+#ifdef BC_TRACE
+            if (c == 0 && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t >= 100 && t < 164) p.trace[(t - 100) * 8 + 6] = spins;
+#endif
+            POLL_FENCE();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+          }
+          if (c == 0) LTRACE(0);
+          const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
+          mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
+          mbar_expect_tx(bar_full + 8u * slot, slot_bytes);
+#pragma unroll
+          for (int sp = 0; sp < 2; ++sp)
+            bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
+                          src + (size_t)sp * (H / 8) * LM * 8 + (size_t)c * (KC / 8) * LM * 8, chunk_split, bar_full + 8u * slot);
+        }
+        LTRACE(1);
+      }
+    }
+  } else if (warp == 2) {
+    // ======================= relay: "landed in this CTA" -> the leader's barriers =======================
+    if (lane == 0) {
+      mbar_wait(bar_w, 0);
+      mbar_arrive_leader(bar_wr);
+      const uint32_t total = (uint32_t)p.T * (uint32_t)nchunks;
+      for (uint32_t cc = 0; cc < total; ++cc) {
+        const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
+        mbar_wait(bar_full + 8u * slot, use & 1u);
+        mbar_arrive_leader(bar_ready + 8u * slot);
+
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issue: the leader's elected lane, M = 256 over both tiles =======================
+    if (rank == 0 && elect_one()) {
+      mbar_wait_cluster(bar_wr, 0);
+      const uint32_t a_plane = LM * 16u;
+      const uint32_t hi_d = desc_hi(128u);
+      const uint32_t idesc_x = idesc_bf16_m256(2 * PNS), idesc_y = idesc_bf16_m256(PNS);
+      const uint32_t bx0 = desc_lo(smem_u32(sW), (uint32_t)PNS * 16u);                   // k-planes 64 rows apart
+      const uint32_t by0 = desc_lo(smem_u32(sW) + x_bytes, (uint32_t)PNS * 8u);          // k-planes 32 rows apart
+      const uint32_t a_g = (2u * a_plane) >> 4, bx_g = (2u * PNS * 16u) >> 4, by_g = (2u * PNS * 8u) >> 4;
+      uint32_t cc = 0;
+      for (int t = 0; t < p.T; ++t) {
+        mbar_wait_cluster(bar_acce, ((uint32_t)t & 1u) ^ 1u);      // both CTAs' gate warps have drained step t-1
+        tc_fence_after();
+        for (int c = 0; c < nchunks; ++c, ++cc) {
+          const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
+          mbar_wait_cluster(bar_ready + 8u * slot, use & 1u);
+          tc_fence_after();
+          uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes, a_plane);
+          uint32_t bx = bx0 + (uint32_t)c * (KC / 16) * bx_g, by = by0 + (uint32_t)c * (KC / 16) * by_g;
+#pragma unroll
+          for (int g = 0; g < KC / 16; ++g, a_lo += a_g, bx += bx_g, by += by_g) {
+            mma2_bf16_rt(tmem_base, a_lo, bx, hi_d, hi_d, idesc_x, (g | c) ? 1u : 0u);   // a_hi x [w_hi | w_lo]
+            mma2_bf16_raw<true>(tmem_base, a_lo + (chunk_split >> 4), by, hi_d, hi_d, idesc_y);   // a_lo x w_hi
+          }
+          umma_commit_pair(bar_empty + 8u * slot);
+        }
+        umma_commit_pair(bar_accf);
+        LTRACE(2);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================= gate warps: 32 rows x 4 units x 4 gates per thread =======================
+    constexpr int UPW = 4;
+    const int gw = warp - 4;
+    const int q = warp & 3;
+    const int ug = gw >> 2;                              // units 4*ug .. 4*ug + 3 of the pair slice
+    const int row = q * 32 + lane;
+    const int u_glb = S * U + ug * UPW;
+    const uint32_t col0 = (uint32_t)((ug >> 1) * 32 + (ug & 1) * UPW);   // column of (gate 0, first unit): 32-column slice, then gate-major
+    const int b = m * LM + row;
+    const bool row_ok = b < p.B;
+    const float* pre_row = p.pre + (size_t)(row_ok ? b : 0) * p.pre_rows * 4 * H + u_glb;
+    const size_t out_row = (size_t)(row_ok ? b : 0) * p.y_rows * H + u_glb;
+    const size_t hx_off = (size_t)m * hx_tile + ((size_t)(u_glb >> 3) * LM + row) * 8 + (u_glb & 7);
+    unsigned int* counter = p.counters + m * CNT_STRIDE + (S * U) / KC;
+    float c_state[UPW], pg[4][UPW];
+#pragma unroll
+    for (int u = 0; u < UPW; ++u) c_state[u] = (p.c_state && p.t_base > 0 && row_ok) ? p.c_state[(size_t)b * H + u_glb + u] : 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 v = row_ok ? __ldcs(reinterpret_cast<const float4*>(pre_row + (size_t)g * H)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pg[g][0] = v.x; pg[g][1] = v.y; pg[g][2] = v.z; pg[g][3] = v.w;
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col0;
+    for (int t = 0; t < p.T; ++t) {
+      mbar_wait(bar_accf, (uint32_t)t & 1u);
+      tc_fence_after();
+      if (gw == 0 && lane == 0) LTRACE(3);
+      uint32_t acc[2][4][UPW];
+#pragma unroll
+      for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(acc[sp][g][0]), "=r"(acc[sp][g][1]), "=r"(acc[sp][g][2]), "=r"(acc[sp][g][3])
+                       : "r"(taddr + (uint32_t)(sp * PNS + g * 8)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_acce);
+      float hv[UPW];
+#pragma unroll
+      for (int u = 0; u < UPW; ++u) {
+        float a4[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) a4[g] = (__uint_as_float(acc[0][g][u]) + __uint_as_float(acc[1][g][u])) + pg[g][u];
+        const float c = fmaf(sigmoid_acc(a4[1]), c_state[u], sigmoid_acc(a4[0]) * tanh_acc(a4[2]));
+        c_state[u] = c;
+        hv[u] = sigmoid_acc(a4[3]) * tanh_acc(c);
+      }
+      {
+        __nv_bfloat16* dst = p.hx + (size_t)((p.t_base + t) & 1) * hx_parity + hx_off;
+        __nv_bfloat16 hi[UPW], lo[UPW];
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) {
+          hi[u] = __float2bfloat16_rn(hv[u]);
+          lo[u] = __float2bfloat16_rn(hv[u] - __bfloat162float(hi[u]));
+        }
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint2*>(lo);
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      if (gw == 0 && lane == 0) LTRACE(4);
+      asm volatile("bar.sync 1, %0;" ::"n"(GATE_WARPS * 32) : "memory");
+      if (gw == 0 && lane == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        LTRACE(5);
+      }
+      if (t + 1 < p.T) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 v = row_ok ? __ldcs(reinterpret_cast<const float4*>(pre_row + (size_t)(t + 1) * 4 * H + (size_t)g * H)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pg[g][0] = v.x; pg[g][1] = v.y; pg[g][2] = v.z; pg[g][3] = v.w;
+        }
+      }
+      if (row_ok) {
+        const size_t o = out_row + (size_t)t * H;
+        float4 v = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        if (p.skip) {
+          const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.skip + o));
+          v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+        }
+        __stcs(reinterpret_cast<float4*>(p.y + o), v);
+      }
+    }
+    if (p.c_state && row_ok) {
+#pragma unroll
+      for (int u = 0; u < UPW; ++u) p.c_state[(size_t)b * H + u_glb + u] = c_state[u];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // nobody frees TMEM / exits while the peer may still signal or read
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(acc_cols) : "memory");
+}
+
 long long* g_lstm_trace = nullptr;
 
 struct LstmTcPlan {
   int NS, nslot, n_slices, m_tiles, split, tpc, grid_y;
-  size_t smem, hx_bytes, ws_bytes;
+  int pair, pair_nslot;          // CTA-pair form: 1 = use lstm_pair_kernel (grid 2 * n_slices / 2 x m_tiles / 2)
+  size_t smem, hx_bytes, ws_bytes, pair_smem;
 };
 
 int device_sms() {
@@ -393,6 +671,19 @@ bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   const int side_by_side = device_sms() / pl->n_slices;
   pl->tpc = (pl->m_tiles > side_by_side && bc::policy().lstm_pingpong) ? 2 : 1;
   pl->grid_y = (pl->m_tiles + pl->tpc - 1) / pl->tpc;
+  // CTA pairs where one tile per CTA no longer fits side by side: an even number of tiles, 64-column pair slices
+  pl->pair = 0; pl->pair_nslot = 0; pl->pair_smem = 0;
+  if (pl->split == 2 && bc::policy().lstm_pair && pl->m_tiles > side_by_side && pl->m_tiles % 2 == 0 && pl->n_slices % 2 == 0 &&
+      (pl->n_slices / 2) * pl->m_tiles <= device_sms()) {
+    const size_t wp = (size_t)(PNS + PNS / 2) * H * 2;
+    int ns = H / KC;
+    while (ns > 2 && wp + ns * slot + 512 > 227 * 1024) --ns;
+    if (wp + ns * slot + 512 <= 227 * 1024) {
+      pl->pair = 1;
+      pl->pair_nslot = ns;
+      pl->pair_smem = wp + ns * slot + (3 * ns + 4) * 8 + 64;
+    }
+  }
   return true;
 }
 
@@ -449,6 +740,26 @@ static int lstm_tc_launch(const float* pre, const void* w_image, const float* sk
   cudaError_t e = t_base == 0 ? cudaMemsetAsync(workspace, 0, pl.ws_bytes, st)
                               : cudaMemsetAsync(reinterpret_cast<uint8_t*>(workspace) + hx_pad, 0, pl.ws_bytes - hx_pad, st);
   if (e != cudaSuccess) return bc::cuda_check(e, "cudaMemsetAsync(lstm_tc)");
+  if (pl.pair) {
+    static bool configured[64] = {false};
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      e = cudaFuncSetAttribute(lstm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.pair_smem);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaFuncSetAttribute(lstm_pair)");
+      // every CTA waits for the others: all clusters must be co-resident
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(pl.n_slices, pl.m_tiles / 2); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = pl.pair_smem;
+      int clusters = 0;
+      e = cudaOccupancyMaxActiveClusters(&clusters, lstm_pair_kernel, &cfg);
+      if (e != cudaSuccess) return bc::cuda_check(e, "cudaOccupancyMaxActiveClusters(lstm_pair)");
+      if (clusters * 2 < pl.n_slices * (pl.m_tiles / 2))
+        return bc::fail(BC_EUNSUPPORTED, "lstm_tc(pair): %d CTA pairs do not fit the device side by side (%d)", pl.n_slices * pl.m_tiles / 4, clusters);
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    p.nslot = pl.pair_nslot;
+    lstm_pair_kernel<<<dim3(pl.n_slices, pl.m_tiles / 2), L_THREADS, pl.pair_smem, st>>>(p);
+    BC_LAUNCH_CHECK("lstm_pair_kernel");
+    return BC_OK;
+  }
   void* kern = nullptr;
   if (pl.split == 2) kern = pl.tpc == 2 ? (void*)lstm_tc_kernel<2, 2, 2> : (void*)lstm_tc_kernel<2, 2, 1>;
   else               kern = pl.tpc == 2 ? (void*)lstm_tc_kernel<1, 4, 2> : (void*)lstm_tc_kernel<1, 4, 1>;
@@ -475,7 +786,7 @@ extern "C" int bc_lstm_tc_recurrent_chunk_fwd(const float* pre, const void* w_im
 extern "C" int bc_lstm_tc_ctas(int B, int H, int precision) {
   LstmTcPlan pl;
   if (B <= 0 || !lstm_tc_plan(B, H, precision, &pl)) return 0;
-  return pl.n_slices * pl.grid_y;
+  return pl.pair ? (pl.n_slices / 2) * pl.m_tiles : pl.n_slices * pl.grid_y;
 }
 
 // debug hook (not part of the product path): device buffer of 64*8 int64 receiving clock64 stamps of CTA (0,0)

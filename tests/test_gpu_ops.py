@@ -696,3 +696,37 @@ def test_stream_conv_other_tensor_map_modes(mode):
                        env=env, capture_output=True, text=True, timeout=900, cwd=repo)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1000:]
+
+
+_LSTM_PAIR_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {repo!r})
+from audiotokenization_b200 import _cabi, ops
+from audiotokenization_b200.vq import module as M
+assert "lstm_pair=1" in _cabi.policy(), _cabi.policy()
+for H, B, T in ((512, 512, 40), (512, 400, 33), (256, 1024, 12)):
+    g = torch.Generator().manual_seed(H + B + T)
+    m = M.ResLSTM(H, num_layers=1).cuda()
+    img = m.lstm.recurrent_image_for(0, "bf16x3")
+    pre = (torch.randn(B, T, 4 * H, generator=g) * 0.7).cuda()
+    skip = torch.randn(B, T, H, generator=g).cuda()
+    n_slices = ops.lstm_tc_ctas(128, H, "bf16x3")                       # one tile: one CTA per 32-column slice
+    small = 128 * (148 // n_slices)                                     # what fits side by side with one tile per CTA
+    assert B > small and ops.lstm_tc_ctas(B, H, "bf16x3") == (n_slices // 2) * ((B + 127) // 128)     # the pair plan
+    got = ops.lstm_recurrent_tc(pre, img, skip, "bf16x3", ops.lstm_tc_max_batch(H, "bf16x3"))
+    want = ops.lstm_recurrent_tc(pre, img, skip, "bf16x3", small)
+    assert torch.isfinite(got).all() and torch.equal(got, want), (H, B, T)
+    print("lstm pair ok", H, B, T)
+"""
+
+
+def test_res_lstm_cta_pair_recurrence_is_bit_identical():
+    """lstm_pair_kernel (tcgen05 cta_group::2: two batch tiles x 64 gate columns per CTA pair; opt-in with BC_LSTM_PAIR=1,
+    hence the subprocess) accumulates the same products in the same order as the one-tile-per-CTA kernel, so it must
+    reproduce it (the same rows in launches that fit side by side) bit for bit -- partial last tile included."""
+    import os, subprocess, sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _LSTM_PAIR_SCRIPT.format(repo=repo)], env=dict(os.environ, BC_LSTM_PAIR="1"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("lstm pair ok") == 3, r.stdout
