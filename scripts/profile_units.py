@@ -17,10 +17,10 @@ for C, dil, T in ((32, 9, 480000), (64, 9, 240000), (128, 9, 60000), (256, 9, 12
         y = m.forward_cl(x)
     torch.cuda.synchronize()
     del x, y, m
-for ci, co, k, s, T in ((32, 64, 4, 2, 480000), (512, 512, 3, 1, 2400 * 64)):
+for ci, co, k, s, T in ((32, 64, 4, 2, 480000), (512, 512, 3, 1, 2400 * 64), (512, 2048, 1, 1, 2400 * 64)):
     pad = (s // 2 + s % 2) if s > 1 else (k - 1) // 2
     m = M.WNConv1d(ci, co, kernel_size=k, stride=s, padding=pad).cuda()
-    act = activations.SnakeBeta(ci, alpha_logscale=True).cuda()
+    act = activations.SnakeBeta(ci, alpha_logscale=True).cuda() if k > 1 else None
     x = torch.randn(clips if s > 1 else 1, T, ci, device="cuda")
     for _ in range(2):
         y = m.forward_cl(x, act=act)

@@ -88,7 +88,9 @@ def traffic(path, out_json, precision):
     agg = {}
     for r in rd:
         name = r["Kernel Name"]
-        name = name.replace("conv_stream_pair_kernel", "conv_stream_kernel")   # one family, two forms (bench.py's label)
+        for form in ("conv_stream_tma_pair_kernel", "conv_stream_tma_kernel", "conv_stream_pair_kernel"):
+            name = name.replace(form, "conv_stream_kernel")   # one family, four forms (bench.py's label)
+        name = name.replace("lstm_pair_kernel", "lstm_tc_kernel")
         fam = next((f for f in ("conv_stream_kernel", "ru_persist_kernel", "ru_group_kernel", "ru_pair_kernel", "conv1d_tc_kernel",
                                 "conv1d_f32_kernel", "lstm_tc_kernel", "stem_conv", "tail_conv", "vq_scan_kernel", "vq_encode_kernel", "snake_aa2_kernel",
                                 "snake_kernel") if f in name), None)
