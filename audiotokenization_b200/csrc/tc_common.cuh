@@ -222,6 +222,16 @@ __device__ __forceinline__ f32x2 snake_bf2(f32x2 x, f32x2 a, f32x2 ib) {
   return fma2(ib, mul2(s, s), x);
 }
 
+// SnakeBeta of the tensor-core prologues / MID stages.  BC_SNAKE_REDUCE = 1 keeps the explicit range reduction in split
+// precision (absolute error of sin independent of |x*a|); 0 (default) feeds the SFU the raw product in both modes.  The SFU's
+// own reduction works on the product rounded to turns, so its error grows like |x*a| * 1.2e-7 rad -- but y = x + sin^2/b then
+// carries a RELATIVE error of at most 1.2e-7 * (a/b), because |x*a| large means |x| large: two orders below the 2^-17
+// relative error of the hi/lo split that follows, at half the FMA-pipe work per element (4 instead of 8 operations; the
+// producers and MID stages are bound by exactly this arithmetic).  The exact-fp32 kernels and the anti-aliased
+// stencil keep the reduced form.
+#ifndef BC_SNAKE_REDUCE
+#define BC_SNAKE_REDUCE 0
+#endif
 template <int SPLIT>
 __device__ __forceinline__ void snake8(float v[8], const float4& a0, const float4& a1, const float4& b0, const float4& b1) {
   const f32x2 aa[4] = {pack2(a0.x, a0.y), pack2(a0.z, a0.w), pack2(a1.x, a1.y), pack2(a1.z, a1.w)};
@@ -229,7 +239,7 @@ __device__ __forceinline__ void snake8(float v[8], const float4& a0, const float
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const f32x2 x = pack2(v[2 * e], v[2 * e + 1]);
-    const f32x2 y = SPLIT == 2 ? snake_tc2(x, aa[e], bb[e]) : snake_bf2(x, aa[e], bb[e]);
+    const f32x2 y = (SPLIT == 2 && BC_SNAKE_REDUCE) ? snake_tc2(x, aa[e], bb[e]) : snake_bf2(x, aa[e], bb[e]);
     unpack2(y, v[2 * e], v[2 * e + 1]);
   }
 }
@@ -258,8 +268,8 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 // four elements (one 16-byte load): the producers of the streamed-weight kernel
 template <int SPLIT>
 __device__ __forceinline__ void snake4(float4& v, const float4& a, const float4& b) {
-  const f32x2 y0 = SPLIT == 2 ? snake_tc2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y)) : snake_bf2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y));
-  const f32x2 y1 = SPLIT == 2 ? snake_tc2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w)) : snake_bf2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w));
+  const f32x2 y0 = (SPLIT == 2 && BC_SNAKE_REDUCE) ? snake_tc2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y)) : snake_bf2(pack2(v.x, v.y), pack2(a.x, a.y), pack2(b.x, b.y));
+  const f32x2 y1 = (SPLIT == 2 && BC_SNAKE_REDUCE) ? snake_tc2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w)) : snake_bf2(pack2(v.z, v.w), pack2(a.z, a.w), pack2(b.z, b.w));
   unpack2(y0, v.x, v.y);
   unpack2(y1, v.z, v.w);
 }
