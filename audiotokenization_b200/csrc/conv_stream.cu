@@ -364,7 +364,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
       // a phantom tile (pair form, odd tile count) is staged as if it lay entirely beyond the item: all zeros
       const int g0row = tp.valid ? t0 * p.stride - p.pad_left + (tp.nt >= p.nt_shift ? 1 : 0) : p.T_in + p.slab_rows;
       const float* xb = p.x + (size_t)b * p.T_in * p.C_in + c4 * 4;
-      long long wE = 0, wL = 0, wM = 0, wS = 0;
+      long long wE = 0, wL = 0, wM = 0, wS = 0, wQ = 0;
       for (int g = 0; g < p.groups; ++g, ++sq) {
         const int slot = slot_c, use = use_c;
         if (++slot_c == p.NA) { slot_c = 0; ++use_c; }
@@ -402,14 +402,28 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
             if (p.stride > 1) { const int r = c * p.x_rows + r_first; rr = r / p.stride; ph = r - rr * p.stride; }
             for (int i0 = r_first; i0 < p.x_rows; i0 += rstep * P_BATCH) {
               float4 v4[P_BATCH];
+              if (DBG_SKIP(1)) break;                    // timing experiment: no loads, math or stores
+              const long long tq0_ = STRACE_ON ? clock64() : 0;
 #pragma unroll
               for (int j = 0; j < P_BATCH; ++j)
                 if (i0 + rstep * j < p.x_rows) v4[j] = *reinterpret_cast<const float4*>(src + (size_t)(i0 + rstep * j) * xpitch);
+              if (STRACE_ON) {
+                float acc_ = 0.f;
+#pragma unroll
+                for (int j = 0; j < P_BATCH; ++j) if (i0 + rstep * j < p.x_rows) acc_ += v4[j].x;
+                if (acc_ == 1.2345e-30f) ++wE;
+                wQ += clock64() - tq0_;                  // shared-memory loads landed
+              }
 #pragma unroll
               for (int j = 0; j < P_BATCH; ++j) {
                 if (i0 + rstep * j < p.x_rows) {
                   float4 v = v4[j];
-                  if (snake) snake4<SPLIT>(v, sa, sb);   // snake(0) == 0: rows outside the item stay zero
+                  if (snake && !DBG_SKIP(32)) snake4<SPLIT>(v, sa, sb);   // snake(0) == 0: rows outside the item stay zero
+                  if (DBG_SKIP(64)) {                    // timing experiment: raw bytes instead of the hi/lo split
+                    uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
+                    *reinterpret_cast<float2*>(d_) = make_float2(v.x, v.y);
+                    *reinterpret_cast<float2*>(d_ + a_split) = make_float2(v.z, v.w);
+                  } else
                   store_quad<SPLIT>(v, dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u, a_split);
                 }
                 ph += ph_step; rr += rr_step;
@@ -519,7 +533,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
         if (lane == 0) ARRIVE_MMA(BAR(B_A_FULL + slot));
         if (g == p.groups - 1 && tw == 0) STRACE(1);
       }
-      if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) { p.trace[it * 16 + 12] = wE; p.trace[it * 16 + 13] = wL; p.trace[it * 16 + 14] = wM; p.trace[it * 16 + 15] = wS; }
+      if (STRACE_ON && blockIdx.x == 0 && it < 64 && warp == 0 && lane == 0) { p.trace[it * 16 + 12] = wE; p.trace[it * 16 + 13] = wL; p.trace[it * 16 + 14] = wM; p.trace[it * 16 + 15] = wS; p.trace[it * 16 + 11] = wQ; }
     }
   } else if (warp >= LOAD_WARP) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R::REG_CTRL));
@@ -1014,6 +1028,10 @@ bool stream_plan_tma(int C_in, int K, int stride, int dilation, StreamPlan* pl, 
   const int N = pl->N, split = pl->split;
   pl->slab_rows = (BM - 1) * stride + (K - 1) * dilation + 1;
   pl->rpp = (pl->slab_rows + stride - 1) / stride;
+  // stride 2: a half-warp of a producer store covers rows r .. r+3 = two rows of each phase; the phases' blocks must sit
+  // 32 bytes apart modulo 64 (rpp = 2 mod 4) or the two 32-byte pieces overlap in the banks (ncu: 308 store conflicts per
+  // tile of the 32 -> 64 conv with rpp = 129).  Strides 4 and 5 want rpp = 1 mod 4, which 129 already is.
+  if (stride == 2) while (pl->rpp % 4 != 2) ++pl->rpp;
   pl->x_rows = stride > 1 ? pl->rpp : pl->slab_rows;       // one box per phase-sized run of slab rows
   pl->x_nbox = stride > 1 ? stride : 1;
   if (pl->x_rows > 256) return false;                      // TMA box limit
@@ -1150,6 +1168,10 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   pl->unit_bytes = (uint32_t)tpu * pl->tap_bytes;
   pl->slab_rows = (BM - 1) * stride + (K - 1) * dilation + 1;
   pl->rpp = (pl->slab_rows + stride - 1) / stride;
+  // stride 2: a half-warp of a producer store covers rows r .. r+3 = two rows of each phase; the phases' blocks must sit
+  // 32 bytes apart modulo 64 (rpp = 2 mod 4) or the two 32-byte pieces overlap in the banks (ncu: 308 store conflicts per
+  // tile of the 32 -> 64 conv with rpp = 129).  Strides 4 and 5 want rpp = 1 mod 4, which 129 already is.
+  if (stride == 2) while (pl->rpp % 4 != 2) ++pl->rpp;
   // plane stride: rows * 16 B, padded so a group's two 8-channel planes sit 64 bytes apart modulo 128
   pl->plane_bytes = (uint32_t)stride * pl->rpp * 16u;
   while (pl->plane_bytes % 128u != 64u) pl->plane_bytes += 16u;

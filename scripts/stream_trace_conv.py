@@ -40,5 +40,5 @@ d = (t[6:n, 9] - t[5:n - 1, 9]).float()
 print("steady-state cycles per tile (store_done deltas):", float(d.mean()))
 for a, b, label in [(0, 1, "PRODUCE tile"), (2, 3, "MMA conv issue span"), (8, 9, "STORE after acc"), (1, 2, "p_done -> m_go"), (3, 8, "m_iss -> st_acc")]:
     print(f"  {label:24s} {float((t[5:n, b] - t[5:n, a]).float().mean()):8.0f} cycles")
-print(f"  producer warp 0, per tile it produced a group of: load wait {float(t[5:n, 13].float().mean()):8.0f}  math+stores {float(t[5:n, 14].float().mean()):8.0f}  incl. warp sync {float(t[5:n, 15].float().mean()):8.0f}")
+print(f"  producer warp 0, per tile it produced a group of: load wait {float(t[5:n, 13].float().mean()):8.0f}  math+stores {float(t[5:n, 14].float().mean()):8.0f}  incl. warp sync {float(t[5:n, 15].float().mean()):8.0f}  of which LDS batch {float(t[5:n, 11].float().mean()):8.0f}")
 print(f"  MMA warp waits per tile: A {float(t[5:n, 10].float().mean()):8.0f}  B {float(t[5:n, 11].float().mean()):8.0f}   producer team 0 blocked on free slot: {float(t[5:n, 12].float().mean()):8.0f}")
