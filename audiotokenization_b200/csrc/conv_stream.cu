@@ -123,6 +123,7 @@ struct SParams {
   int nt_shift;     // n-tiles >= nt_shift read their taps one row later (pad_left - 1): the q = 1 phases of a transposed conv
   int N, groups, tpu, upg, gpu1;
   int slab_rows, rpp, NA, NB, acc_stages, acc_stride, epi_warps;
+  int NT;           // producer teams (NA % NT == 0): slot s belongs to team s % NT
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes;
   int NX, x_rows, x_nbox, x_gpb;   // TMA form: ring of NX fp32 units [x_rows][16 * x_gpb channels], x_nbox units per (tile, x_gpb groups)
   uint32_t x_unit, x_bytes;        // unit stride in the ring / bytes one box delivers
@@ -269,7 +270,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
   if (tid == 0) {
     constexpr int NCTA = PAIR ? 2 : 1;
     for (int s = 0; s < 4; ++s) {
-      mbar_init(BAR(B_A_FULL + s), NCTA * (N_PROD / p.NA));
+      mbar_init(BAR(B_A_FULL + s), NCTA * (N_PROD / p.NT));
       mbar_init(BAR(B_A_EMPTY + s), 1);
     }
     for (int s = 0; s < 8; ++s) {
@@ -280,7 +281,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
     if (XL) {
       for (int s = 0; s < MAX_NX; ++s) {
         mbar_init(BAR(B_X_FULL + s), 1);
-        mbar_init(BAR(B_X_EMPTY + s), p.x_gpb * (N_PROD / p.NA));
+        mbar_init(BAR(B_X_EMPTY + s), p.x_gpb * (N_PROD / p.NT));
       }
     }
     for (int s = 0; s < 2; ++s) {
@@ -344,9 +345,10 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
     // instead of 32 lines, which keeps the L1 wavefront queue out of the critical path.
     // One team per ring slot (NA teams of PROD_WARPS / NA warps): a slot's barriers then see one producer, which
     // is never more than one phase ahead of them.
-    const int team_warps = N_PROD / p.NA;
+    // TMA form: TWO teams that alternate between two slots each, so a team stages tile i+1 while the MMAs read tile i
+    const int team_warps = N_PROD / p.NT;
     const int team = warp / team_warps, tw = warp - team * team_warps;
-    if (team >= p.NA) goto done;
+    if (team >= p.NT) goto done;
     const int rstep = 8 * team_warps;               // rows covered by one load instruction of the team
     const int c4 = lane & 3;                        // which 4 of the group's 16 channels
     const int r_first = tw * 8 + (lane >> 2);       // slab rows r_first + rstep*j
@@ -368,10 +370,11 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
       for (int g = 0; g < p.groups; ++g, ++sq) {
         const int slot = slot_c, use = use_c;
         if (++slot_c == p.NA) { slot_c = 0; ++use_c; }
+        const bool mine = (p.NT == p.NA ? slot : slot % p.NT) == team;
         if (XL) {
           const int gsub = g % p.x_gpb;             // a unit carries x_gpb neighbouring groups (one team each)
           const bool last_sub = gsub == p.x_gpb - 1;
-          if (slot != team) {           // another team's group: only the ring position moves on
+          if (!mine) {                  // another team's group: only the ring position moves on
             if (last_sub) {
               xslot += (uint32_t)p.x_nbox;
               while (xslot >= (uint32_t)p.NX) { xslot -= (uint32_t)p.NX; xph ^= 1u; }
@@ -443,7 +446,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
           if (g == p.groups - 1 && tw == 0) STRACE(1);
           continue;
         }
-        if (slot != team) continue;
+        if (!mine) continue;
         if (g == 0 && tw == 0) STRACE(0);
         float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
         if (snake) {
@@ -1016,7 +1019,7 @@ int encode_cl_map(CUtensorMap* m, const float* base, int B, int T, int C, int bo
 
 struct StreamPlan {
   int N, n_tiles, groups, tpu, upg, gpu1, slab_rows, rpp, NA, NB, acc_stages, acc_stride, tmem_cols, split, epi_warps;
-  int NX, x_rows, x_nbox, x_gpb;
+  int NX, x_rows, x_nbox, x_gpb, NT;
   uint32_t a_stage, unit_bytes, tap_bytes, plane_bytes, x_unit, x_bytes;
   size_t smem;
 };
@@ -1082,7 +1085,7 @@ bool stream_plan_tma(int C_in, int K, int stride, int dilation, StreamPlan* pl, 
     if (best_na < 2) return false;
     NA = best_na;
     while (Roles<false>::PROD % NA != 0) --NA;
-    pl->NA = NA; pl->NB = best_nb;
+    pl->NA = NA; pl->NB = best_nb; pl->NT = NA;
     pl->acc_stride = N;
     pl->acc_stages = 2 * N <= 512 ? 2 : 1;
     int cols = pl->acc_stages * pl->acc_stride, pw = 32;
@@ -1091,42 +1094,40 @@ bool stream_plan_tma(int C_in, int K, int stride, int dilation, StreamPlan* pl, 
     pl->smem = (size_t)best_nb * pl->unit_bytes + misc + (size_t)NA * pl->a_stage;
     return true;
   }
-  int best_nx = 0;
-  for (uint32_t cap = UNIT_MAX_BYTES; cap >= 16384u && best_nx < want; cap >>= 1) {
-    int tpu = (int)(cap / pl->tap_bytes);
-    if (tpu < 1) tpu = 1;
-    if (tpu > MAX_TPU) tpu = MAX_TPU;
-    if (tpu > K) tpu = K;
-    const int upg = (K + tpu - 1) / tpu;
-    tpu = (K + upg - 1) / upg;
-    const uint32_t unit_bytes = (uint32_t)tpu * pl->tap_bytes;
-    int NB = (int)(98304u / unit_bytes);
-    if (NB > 8) NB = 8;
-    for (; NB >= 3; --NB) {
-      const size_t used = (size_t)NB * unit_bytes + misc + 2 * (size_t)pl->a_stage;
-      if (used >= budget) continue;
-      int nx = (int)((budget - used) / pl->x_unit);
-      if (nx > MAX_NX) nx = MAX_NX;
-      if (nx > best_nx) {
-        best_nx = nx;
-        pl->tpu = tpu; pl->upg = upg; pl->unit_bytes = unit_bytes; pl->NB = NB; pl->NX = nx;
+  // four activation stages (two per team: double buffering against the MMAs) when the rings still fit, else two
+  int best_nx = 0, NA = 0;
+  for (int na = 4; na >= 2 && best_nx < want; na -= 2) {
+    best_nx = 0;
+    for (uint32_t cap = UNIT_MAX_BYTES; cap >= 16384u && best_nx < want; cap >>= 1) {
+      int tpu = (int)(cap / pl->tap_bytes);
+      if (tpu < 1) tpu = 1;
+      if (tpu > MAX_TPU) tpu = MAX_TPU;
+      if (tpu > K) tpu = K;
+      const int upg = (K + tpu - 1) / tpu;
+      tpu = (K + upg - 1) / upg;
+      const uint32_t unit_bytes = (uint32_t)tpu * pl->tap_bytes;
+      int NB = (int)(98304u / unit_bytes);
+      if (NB > 8) NB = 8;
+      for (; NB >= 3; --NB) {
+        const size_t used = (size_t)NB * unit_bytes + misc + (size_t)na * pl->a_stage;
+        if (used >= budget) continue;
+        int nx = (int)((budget - used) / pl->x_unit);
+        if (nx > MAX_NX) nx = MAX_NX;
+        if (nx > best_nx) {
+          best_nx = nx; NA = na;
+          pl->tpu = tpu; pl->upg = upg; pl->unit_bytes = unit_bytes; pl->NB = NB; pl->NX = nx;
+        }
+        if (best_nx >= want) break;
       }
-      if (best_nx >= want) break;
     }
   }
-  if (best_nx < 2) return false;
+  if (best_nx < 2 || NA < 2) return false;
   int gpu1 = 1;
   while (gpu1 * 2 <= pl->tpu && gpu1 * 2 <= 4) gpu1 *= 2;
   pl->gpu1 = gpu1;
-  // what is left goes to more activation stages (= producer teams), up to four
   const size_t used = (size_t)pl->NB * pl->unit_bytes + misc + (size_t)pl->NX * pl->x_unit;
-  int NA = (int)((budget - used) / pl->a_stage);
-  const int groups = C_in / 16;
-  if (NA > 4) NA = 4;
-  if (NA > groups) NA = groups < 2 ? 2 : groups;
-  while (Roles<false>::PROD % NA != 0) --NA;             // teams of Roles<false>::PROD / NA warps
-  if (NA < 2) return false;
   pl->NA = NA;
+  pl->NT = 2;                                            // two teams of six warps; with NA = 4 each alternates between two slots
   pl->acc_stride = N;
   pl->acc_stages = 2 * N <= 512 ? 2 : 1;
   int cols = pl->acc_stages * pl->acc_stride, pw = 32;
@@ -1205,6 +1206,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
   if (NA > 4) NA = 4;
   pl->epi_warps = epi_warps;
   pl->NA = NA;
+  pl->NT = NA;
   pl->NB = NB;
   pl->acc_stride = fused ? 2 * N : N;
   pl->acc_stages = 2 * pl->acc_stride <= 512 ? 2 : 1;
@@ -1219,7 +1221,7 @@ bool stream_plan(int C_in, int C_out, int K, int stride, int dilation, int preci
 
 int launch_stream(SParams& p, const StreamPlan& pl, int fused, cudaStream_t st, bool pair = false, bool tma = false) {
   p.N = pl.N; p.groups = pl.groups; p.tpu = pl.tpu; p.upg = pl.upg; p.gpu1 = pl.gpu1;
-  p.slab_rows = pl.slab_rows; p.rpp = pl.rpp; p.NA = pl.NA; p.NB = pl.NB;
+  p.slab_rows = pl.slab_rows; p.rpp = pl.rpp; p.NA = pl.NA; p.NB = pl.NB; p.NT = pl.NT;
   p.acc_stages = pl.acc_stages; p.acc_stride = pl.acc_stride; p.epi_warps = pl.epi_warps; p.a_stage = pl.a_stage; p.unit_bytes = pl.unit_bytes;
   p.tap_bytes = pl.tap_bytes; p.tmem_cols = pl.tmem_cols; p.plane_bytes = pl.plane_bytes;
   p.NX = pl.NX; p.x_rows = pl.x_rows; p.x_nbox = pl.x_nbox; p.x_gpb = pl.x_gpb; p.x_unit = pl.x_unit; p.x_bytes = pl.x_bytes;

@@ -59,7 +59,13 @@ enum {
 int bc_abi_version(void);
 const char* bc_last_error(void);
 /* Kernel-selection knobs this process runs with (read from the environment once, at first use), as a
- * "key=value ..." string: recorded by bench.py next to every number.  None of them changes results. */
+ * "key=value ..." string: recorded by bench.py next to every number.  None of them changes results
+ * (same arithmetic per element; the forms they select are pinned against each other by the tests):
+ *   BC_RU_GROUP / BC_RU_PERSIST / BC_RU_PAIR = 0   switch off the warpgroup-per-tile / role-pipeline / CTA-pair fused units
+ *   BC_STREAM_PAIR = 0     streamed-weight kernel without the CTA-pair (cta_group::2) form
+ *   BC_STREAM_TMA = 0|1|2  plain streamed convs: no tensor maps | y by TMA stores (default) | x boxes by TMA as well
+ *   BC_LSTM_PINGPONG = 0   one batch tile per CTA only (max batch 256);  BC_LSTM_PAIR = 1  CTA-pair recurrence kernel
+ *   BC_TC_VARIANT / BC_TC_PERSIST   per-tile tcgen05 conv variants (development) */
 int bc_policy(char* buf, size_t n);
 /* 0 if device `dev` exists and is sm_100; fills optional outputs. */
 int bc_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
