@@ -346,9 +346,10 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
     // One team per ring slot (NA teams of PROD_WARPS / NA warps): a slot's barriers then see one producer, which
     // is never more than one phase ahead of them.
     // TMA form: TWO teams that alternate between two slots each, so a team stages tile i+1 while the MMAs read tile i
-    const int team_warps = N_PROD / p.NT;
+    const int n_teams = XL ? p.NT : p.NA;            // (every other form: one team per slot)
+    const int team_warps = N_PROD / n_teams;
     const int team = warp / team_warps, tw = warp - team * team_warps;
-    if (team >= p.NT) goto done;
+    if (team >= n_teams) goto done;
     const int rstep = 8 * team_warps;               // rows covered by one load instruction of the team
     const int c4 = lane & 3;                        // which 4 of the group's 16 channels
     const int r_first = tw * 8 + (lane >> 2);       // slab rows r_first + rstep*j
@@ -370,7 +371,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
       for (int g = 0; g < p.groups; ++g, ++sq) {
         const int slot = slot_c, use = use_c;
         if (++slot_c == p.NA) { slot_c = 0; ++use_c; }
-        const bool mine = (p.NT == p.NA ? slot : slot % p.NT) == team;
+        const bool mine = XL ? (slot % p.NT == team) : (slot == team);
         if (XL) {
           const int gsub = g % p.x_gpb;             // a unit carries x_gpb neighbouring groups (one team each)
           const bool last_sub = gsub == p.x_gpb - 1;
