@@ -22,7 +22,7 @@ static Policy read_policy() {
   e = getenv("BC_STREAM_PAIR");  p.stream_pair = (e && e[0] == '0') ? 0 : 1;
   e = getenv("BC_STREAM_TMA");   p.stream_tma = e ? atoi(e) & 3 : 1;     // 0 off, 1 TMA stores, 2 TMA stores + loads
   e = getenv("BC_LSTM_PINGPONG"); p.lstm_pingpong = (e && e[0] == '0') ? 0 : 1;
-  e = getenv("BC_LSTM_PAIR");    p.lstm_pair = (e && e[0] == '1') ? 1 : 0;     // measured: no gain over the ping-pong form
+  e = getenv("BC_LSTM_PAIR");    p.lstm_pair = e ? atoi(e) & 3 : 0;            // 1: where one tile per CTA does not fit (measured: no gain over the ping-pong form), 2: whenever the tile count is even
   return p;
 }
 const Policy& policy() {

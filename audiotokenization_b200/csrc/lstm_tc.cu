@@ -673,7 +673,7 @@ bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   pl->grid_y = (pl->m_tiles + pl->tpc - 1) / pl->tpc;
   // CTA pairs where one tile per CTA no longer fits side by side: an even number of tiles, 64-column pair slices
   pl->pair = 0; pl->pair_nslot = 0; pl->pair_smem = 0;
-  if (pl->split == 2 && bc::policy().lstm_pair && pl->m_tiles > side_by_side && pl->m_tiles % 2 == 0 && pl->n_slices % 2 == 0 &&
+  if (pl->split == 2 && bc::policy().lstm_pair && (pl->m_tiles > side_by_side || bc::policy().lstm_pair >= 2) && pl->m_tiles % 2 == 0 && pl->n_slices % 2 == 0 &&
       (pl->n_slices / 2) * pl->m_tiles <= device_sms()) {
     const size_t wp = (size_t)(PNS + PNS / 2) * H * 2;
     int ns = H / KC;
