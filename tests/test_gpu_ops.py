@@ -569,6 +569,9 @@ STREAM_CONV_CASES = [
     (64, 64, 1, 1, 1, 0, 2, 513),
     (128, 128, 7, 1, 1, 3, 5, 5000),      # more tiles than SMs: every CTA walks several tiles
     (256, 256, 1, 1, 1, 0, 3, 9000),
+    (32, 64, 4, 2, 1, 1, 3, 10),          # T_out = 5: a store tile larger than the item (TMA clips), stride-2 slab
+    (64, 128, 8, 4, 1, 2, 1, 4),          # one output step
+    (512, 512, 3, 1, 1, 1, 130, 3),       # many tiny items
 ]
 
 
