@@ -43,7 +43,13 @@ struct RgParams {
   int B, T, C, K, dil, pad_left;
   int slab_rows, n_pow2, tiles_per_item, total_tiles, G, tmem_cols;
   uint32_t idesc, group_bytes, a_bytes;
+  long long* trace;   // debug (-DBC_TRACE): [tile iteration < 64][16] clock64 stamps of group 0 of CTA 0
 };
+#ifdef BC_TRACE
+#define GTRACE(ev) do { if (p.trace && blockIdx.x == 0 && g == 0 && gt == 0 && titer < 64) p.trace[titer * 16 + (ev)] = clock64(); } while (0)
+#else
+#define GTRACE(ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory");
@@ -145,12 +151,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
     int b = tile / p.tiles_per_item, tt = tile - b * p.tiles_per_item;
     uint32_t ph = 0;
     bool w_ready = false;
-    for (; tile < p.total_tiles; tile += tstep, tt += tstep, ph ^= 1u) {
+    int titer = 0;
+    (void)titer;
+    for (; tile < p.total_tiles; tile += tstep, tt += tstep, ph ^= 1u, ++titer) {
       while (tt >= p.tiles_per_item) { tt -= p.tiles_per_item; ++b; }
       const int t0 = tt * BM;
       const int g0 = t0 - p.pad_left;
       const float* xb = p.x + (size_t)b * p.T * C;
       // ---- stage: x -> snake1 -> bf16 hi[/lo] slab ----
+      GTRACE(0);
       {
         const float* xcol = xb + pl * 8;
         uint8_t* dst = sA + (size_t)pl * plane_bytes;
@@ -179,8 +188,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           }
         }
       }
+      GTRACE(1);
       fence_async_smem();
       group_sync(g);
+      GTRACE(2);
       // ---- mma7 ----
       if (gw == 0) {
         if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
@@ -213,8 +224,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           res4[i] = (t0 + crow + RPI * i < p.T) ? __ldg(reinterpret_cast<const float4*>(rp + (size_t)RPI * i * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // ---- mid: acc1 -> +b7 -> snake2 -> A2 ----
+      GTRACE(3);
       mbar_wait(bar7, ph);
       tc_fence_after();
+      GTRACE(4);
       {
         uint8_t* dst = sA2 + (size_t)row * 16;
 #pragma unroll
@@ -249,9 +262,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           }
         }
       }
+      GTRACE(5);
       tc_fence_before();
       fence_async_smem();
       group_sync(g);
+      GTRACE(6);
       // ---- mma1 ----
       if (gw == 0) {
         tc_fence_after();
@@ -271,8 +286,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
         __syncwarp();
       }
       // ---- store: acc2 + b1 + x -> y ----
+      GTRACE(7);
       mbar_wait(bar1, ph);          // also: the 1x1 conv has finished reading A2, the K-tap conv the slab -> staging is free
       tc_fence_after();
+      GTRACE(8);
       // The residual never goes through the staging block: it was fetched in the coalesced (row group, 16-byte
       // chunk) mapping, which is also the mapping of the final store, so it is added there, from registers.
       {
@@ -288,8 +305,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           }
         }
       }
+      GTRACE(9);
       tc_fence_before();
       group_sync(g);
+      GTRACE(10);
       {
         float* yp = p.y + ((size_t)b * p.T + t0 + crow) * C + cchunk;
         const float* rp = xb + (size_t)(t0 + crow) * C + cchunk;
@@ -302,6 +321,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
           }
         }
       }
+      GTRACE(11);
       group_sync(g);               // staging reads done before the next tile's slab overwrites it
     }
   }
@@ -343,6 +363,7 @@ bool rg_plan(int C, int K, int dilation, int precision, RgPlan* pl) {
 }  // namespace
 
 namespace bc {
+extern long long* g_ru_trace;
 
 // 0 = not applicable, else the number of warpgroups per CTA
 int ru_group_groups(int C, int K, int dilation, int precision) {
@@ -358,6 +379,7 @@ int resunit_group_fwd(const float* x, const float* w7, const float* b7, const fl
   if (!rg_plan(C, K, dilation, precision, &pl))
     return fail(BC_EUNSUPPORTED, "resunit(group): C=%d K=%d dil=%d not supported", C, K, dilation);
   RgParams p;
+  p.trace = g_ru_trace;
   p.x = x; p.y = y; p.w7 = reinterpret_cast<const uint4*>(w7); p.w1 = reinterpret_cast<const uint4*>(w1);
   p.b7 = b7; p.b1 = b1; p.sa1 = sa1; p.sib1 = sib1; p.sa2 = sa2; p.sib2 = sib2;
   p.B = B; p.T = T; p.C = C; p.K = K; p.dil = dilation; p.pad_left = pad_left;

@@ -466,7 +466,7 @@ size_t ru_smem_bytes(int C, int K, int dil, int split, int nslot) {
 
 namespace bc {
 
-static long long* g_ru_trace = nullptr;
+long long* g_ru_trace = nullptr;   // shared with ru_group.cu (debug)
 
 // 0 = not applicable, else number of smem operand slots the persistent kernel would use
 int ru_persist_slots(int C, int K, int dilation, int precision) {
