@@ -164,6 +164,26 @@ __device__ __forceinline__ void store_quad(const float4& v, uint8_t* d8, uint32_
   }
 }
 
+// the same in two steps (BC_STREAM_PROD_ILP): all the arithmetic of a batch first, branch-free, then the predicated stores
+template <int SPLIT>
+__device__ __forceinline__ void split_quad(const float4& v, uint2& h, uint2& l) {
+  h.x = pack_bf16x2(v.x, v.y); h.y = pack_bf16x2(v.z, v.w);
+  if (SPLIT == 2) {
+    float r0, r1, r2, r3;
+    unpack2(sub2(pack2(v.x, v.y), bf16x2_as_f32x2(h.x)), r0, r1);
+    unpack2(sub2(pack2(v.z, v.w), bf16x2_as_f32x2(h.y)), r2, r3);
+    l.x = pack_bf16x2(r0, r1);
+    l.y = pack_bf16x2(r2, r3);
+  }
+}
+// The producers' per-element chain (SnakeBeta -> split) is latency-bound when few producer warps are active at a time
+// (ncu source view of the 32 -> 64 conv: 24 % of all warp samples in fixed-latency dependency stalls): with
+// `if (row valid) { snake; split; store }` per item the compiler emits one branch-guarded block per item and the chains
+// run one after the other; computing the whole batch unconditionally lets it interleave P_BATCH independent chains.
+#ifndef BC_STREAM_PROD_ILP
+#define BC_STREAM_PROD_ILP 1
+#endif
+
 // (n-tile, item, tile-in-item) of a CTA's current tile, advanced incrementally: the tile loop has no division.
 // Tile order: the n-tiles of one 128-step row tile are NEIGHBOURS (tile = row_tile * n_tiles + nt), so the CTAs that run
 // side by side read the same x tile and it comes from HBM once (n-tile-major order streamed x once per n-tile: 16 times
@@ -409,26 +429,31 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
               if (DBG_SKIP(1)) break;                    // timing experiment: no loads, math or stores
               const long long tq0_ = STRACE_ON ? clock64() : 0;
 #pragma unroll
-              for (int j = 0; j < P_BATCH; ++j)
+              for (int j = 0; j < P_BATCH; ++j) {
                 if (i0 + rstep * j < p.x_rows) v4[j] = *reinterpret_cast<const float4*>(src + (size_t)(i0 + rstep * j) * xpitch);
+                else v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
               if (STRACE_ON) {
                 float acc_ = 0.f;
 #pragma unroll
-                for (int j = 0; j < P_BATCH; ++j) if (i0 + rstep * j < p.x_rows) acc_ += v4[j].x;
+                for (int j = 0; j < P_BATCH; ++j) acc_ += v4[j].x;
                 if (acc_ == 1.2345e-30f) ++wE;
                 wQ += clock64() - tq0_;                  // shared-memory loads landed
               }
+              // branch-free arithmetic of the whole batch, then the predicated stores (see BC_STREAM_PROD_ILP)
+              uint2 hq[P_BATCH], lq[P_BATCH];
+              if (snake && !DBG_SKIP(32)) {              // snake(0) == 0: rows outside the item stay zero
+#pragma unroll
+                for (int j = 0; j < P_BATCH; ++j) snake4<SPLIT>(v4[j], sa, sb);
+              }
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) split_quad<SPLIT>(v4[j], hq[j], lq[j]);
 #pragma unroll
               for (int j = 0; j < P_BATCH; ++j) {
                 if (i0 + rstep * j < p.x_rows) {
-                  float4 v = v4[j];
-                  if (snake && !DBG_SKIP(32)) snake4<SPLIT>(v, sa, sb);   // snake(0) == 0: rows outside the item stay zero
-                  if (DBG_SKIP(64)) {                    // timing experiment: raw bytes instead of the hi/lo split
-                    uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
-                    *reinterpret_cast<float2*>(d_) = make_float2(v.x, v.y);
-                    *reinterpret_cast<float2*>(d_ + a_split) = make_float2(v.z, v.w);
-                  } else
-                  store_quad<SPLIT>(v, dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u, a_split);
+                  uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
+                  *reinterpret_cast<uint2*>(d_) = hq[j];
+                  if (SPLIT == 2) *reinterpret_cast<uint2*>(d_ + a_split) = lq[j];
                 }
                 ph += ph_step; rr += rr_step;
                 if (ph >= p.stride) { ph -= p.stride; ++rr; }
@@ -466,14 +491,32 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
           for (int r0 = r_first; r0 < p.slab_rows; r0 += rstep * P_BATCH, src += P_BATCH * rstride, d8 += P_BATCH * dstep) {
             float4 v4[P_BATCH];
 #pragma unroll
-            for (int j = 0; j < P_BATCH; ++j)
+            for (int j = 0; j < P_BATCH; ++j) {
               if (r0 + rstep * j < p.slab_rows) v4[j] = __ldg(reinterpret_cast<const float4*>(src + j * rstride));
+              else if (BC_STREAM_PROD_ILP) v4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             if (!waited) {
               long long tw_ = STRACE_ON ? clock64() : 0;
               mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
               if (STRACE_ON) wE += clock64() - tw_;
               waited = true;
             }
+            if (BC_STREAM_PROD_ILP) {
+              uint2 hq[P_BATCH], lq[P_BATCH];
+              if (snake) {
+#pragma unroll
+                for (int j = 0; j < P_BATCH; ++j) snake4<SPLIT>(v4[j], sa, sb);
+              }
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) split_quad<SPLIT>(v4[j], hq[j], lq[j]);
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) {
+                if (r0 + rstep * j < p.slab_rows) {
+                  *reinterpret_cast<uint2*>(d8 + j * dstep) = hq[j];
+                  if (SPLIT == 2) *reinterpret_cast<uint2*>(d8 + j * dstep + a_split) = lq[j];
+                }
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < P_BATCH; ++j) {
               if (r0 + rstep * j < p.slab_rows) {
@@ -483,6 +526,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
                 }
                 store_quad<SPLIT>(v, d8 + j * dstep, a_split);
               }
+            }
             }
           }
         } else {
@@ -516,6 +560,25 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
               wL += t2_ - tl_;
               tl_ = t2_;
             }
+            if (BC_STREAM_PROD_ILP) {
+              uint2 hq[P_BATCH], lq[P_BATCH];
+              if (snake) {   // snake(0) == 0: padding rows stay zero
+#pragma unroll
+                for (int j = 0; j < P_BATCH; ++j) snake4<SPLIT>(v4[j], sa, sb);
+              }
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) split_quad<SPLIT>(v4[j], hq[j], lq[j]);
+#pragma unroll
+              for (int j = 0; j < P_BATCH; ++j) {
+                if (r0 + rstep * j < p.slab_rows) {
+                  uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
+                  *reinterpret_cast<uint2*>(d_) = hq[j];
+                  if (SPLIT == 2) *reinterpret_cast<uint2*>(d_ + a_split) = lq[j];
+                }
+                ph += ph_step; rr += rr_step;
+                if (ph >= p.stride) { ph -= p.stride; ++rr; }
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < P_BATCH; ++j) {
               if (r0 + rstep * j < p.slab_rows) {
@@ -527,6 +590,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
               }
               ph += ph_step; rr += rr_step;
               if (ph >= p.stride) { ph -= p.stride; ++rr; }
+            }
             }
             if (STRACE_ON) wM += clock64() - tl_;
           }

@@ -21,6 +21,9 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 
+#ifndef BC_RU_ILP     // 1: branch-free staging batches (conv_stream.cu); measured 1 % slower here -> 0: one guarded block per item
+#define BC_RU_ILP 0
+#endif
 namespace {
 using namespace bc::tc;
 
@@ -177,6 +180,25 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
               hi4[j] = lo4[j];
             }
           }
+#if BC_RU_ILP
+          // all the arithmetic of the batch first, branch-free (rows beyond the slab hold zeros), then the predicated stores:
+          // the compiler interleaves the SB independent SnakeBeta -> split chains instead of running one guarded block per item
+          uint4 hq[SB], lq[SB];
+#pragma unroll
+          for (int j = 0; j < SB; ++j) {
+            float v[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
+            snake8<SPLIT>(v, a0, a1, b0, b1);
+            split8<SPLIT>(v, hq[j], lq[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < SB; ++j) {
+            const int r = r0 + PRS * j;
+            if (r < p.slab_rows) {
+              *reinterpret_cast<uint4*>(dst + (size_t)r * 16) = hq[j];
+              if (SPLIT == 2) *reinterpret_cast<uint4*>(dst + (size_t)r * 16 + a_split) = lq[j];
+            }
+          }
+#else
 #pragma unroll
           for (int j = 0; j < SB; ++j) {
             const int r = r0 + PRS * j;
@@ -186,6 +208,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) ru_group_kernel(const RgParams 
               split_store<SPLIT>(v, dst + (size_t)r * 16, a_split);
             }
           }
+#endif
         }
       }
       GTRACE(1);

@@ -21,6 +21,9 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 
+#ifndef BC_RU_ILP     // 1: branch-free staging batches (what made the conv_stream producers 6-15 % faster); measured 1-2 % SLOWER here -> 0: one guarded block per item
+#define BC_RU_ILP 0
+#endif
 namespace {
 using namespace bc::tc;
 
@@ -246,6 +249,25 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
           waited = true;
           if (gtid == 0) TRACE(1);
         }
+#if BC_RU_ILP
+        // arithmetic of the whole batch first, branch-free (items beyond the slab hold zeros), then the predicated stores:
+        // LD_BATCH independent SnakeBeta -> split chains interleave instead of one guarded block per item
+        uint4 hq[LD_BATCH], lq[LD_BATCH];
+#pragma unroll
+        for (int j = 0; j < LD_BATCH; ++j) {
+          float v[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
+          snake8<SPLIT>(v, a0, a1, b0, b1);
+          split8<SPLIT>(v, hq[j], lq[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < LD_BATCH; ++j) {
+          const int i = i0 + j * gthreads;
+          if (i < items) {
+            *reinterpret_cast<uint4*>(dstA + (size_t)(i >> pshift) * 16) = hq[j];
+            if (SPLIT == 2) *reinterpret_cast<uint4*>(dstA + (size_t)(i >> pshift) * 16 + a_split) = lq[j];
+          }
+        }
+#else
 #pragma unroll
         for (int j = 0; j < LD_BATCH; ++j) {
           const int i = i0 + j * gthreads;
@@ -255,6 +277,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) ru_persist_kernel(const RuParam
             split_store<SPLIT>(v, dstA + (size_t)(i >> pshift) * 16, a_split);
           }
         }
+#endif
       }
       if (!waited) mbar_wait(BAR(B_A_EMPTY + slot), (uint32_t)((use & 1) ^ 1));
       fence_async_smem();

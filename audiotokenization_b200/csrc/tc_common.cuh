@@ -165,6 +165,24 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
 // bf16 hi halves of two floats as the two fp32 values they represent
 __device__ __forceinline__ f32x2 bf16x2_as_f32x2(uint32_t h) { return pack2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)); }
 
+// 8 fp32 values -> the bf16 hi (and lo = v - hi) halves of one 16-byte K-major row chunk, in registers
+template <int SPLIT>
+__device__ __forceinline__ void split8(const float v[8], uint4& h, uint4& l) {
+  h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+  h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
+  if (SPLIT == 2) {
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+    uint32_t ll[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r0, r1;
+      unpack2(sub2(pack2(v[2 * e], v[2 * e + 1]), bf16x2_as_f32x2(hh[e])), r0, r1);   // exact: v - bf16(v)
+      ll[e] = pack_bf16x2(r0, r1);
+    }
+    l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+}
+
 template <int SPLIT>
 __device__ __forceinline__ void split_store(const float v[8], uint8_t* dst, uint32_t lo_offset) {
   uint4 h;
