@@ -183,6 +183,9 @@ __device__ __forceinline__ void split_quad(const float4& v, uint2& h, uint2& l) 
 #ifndef BC_STREAM_PROD_ILP
 #define BC_STREAM_PROD_ILP 1
 #endif
+#ifndef BC_STREAM_MCHUNK
+#define BC_STREAM_MCHUNK 4
+#endif
 
 // (n-tile, item, tile-in-item) of a CTA's current tile, advanced incrementally: the tile loop has no division.
 // Tile order: the n-tiles of one 128-step row tile are NEIGHBOURS (tile = row_tile * n_tiles + nt), so the CTAs that run
@@ -269,6 +272,7 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
   using R = Roles<FUSE>;
   constexpr int N_PROD = R::PROD, MID_WARP0 = R::MID0, EPI_WARP0 = R::EPI0, LOAD_WARP = R::LOAD, MMA_WARP = R::MMA;
   constexpr int S_THREADS = R::THREADS, P_BATCH = R::PB;
+  constexpr int M_CHUNK = P_BATCH <= 6 ? P_BATCH : BC_STREAM_MCHUNK;   // chains interleaved at a time (bounds the registers of a long batch)
   const uint32_t plane_bytes = p.plane_bytes;
   const uint32_t a_split = 2u * plane_bytes;
   const uint32_t a2_split = (uint32_t)(A2_CH / 8) * A2_PLANE;
@@ -502,18 +506,21 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
               waited = true;
             }
             if (BC_STREAM_PROD_ILP) {
-              uint2 hq[P_BATCH], lq[P_BATCH];
-              if (snake) {
 #pragma unroll
-                for (int j = 0; j < P_BATCH; ++j) snake4<SPLIT>(v4[j], sa, sb);
-              }
+              for (int j0 = 0; j0 < P_BATCH; j0 += M_CHUNK) {     // M_CHUNK independent chains at a time
+                uint2 hq[M_CHUNK], lq[M_CHUNK];
+                if (snake) {
 #pragma unroll
-              for (int j = 0; j < P_BATCH; ++j) split_quad<SPLIT>(v4[j], hq[j], lq[j]);
+                  for (int j = 0; j < M_CHUNK; ++j) if (j0 + j < P_BATCH) snake4<SPLIT>(v4[j0 + j], sa, sb);
+                }
 #pragma unroll
-              for (int j = 0; j < P_BATCH; ++j) {
-                if (r0 + rstep * j < p.slab_rows) {
-                  *reinterpret_cast<uint2*>(d8 + j * dstep) = hq[j];
-                  if (SPLIT == 2) *reinterpret_cast<uint2*>(d8 + j * dstep + a_split) = lq[j];
+                for (int j = 0; j < M_CHUNK; ++j) if (j0 + j < P_BATCH) split_quad<SPLIT>(v4[j0 + j], hq[j], lq[j]);
+#pragma unroll
+                for (int j = 0; j < M_CHUNK; ++j) {
+                  if (j0 + j < P_BATCH && r0 + rstep * (j0 + j) < p.slab_rows) {
+                    *reinterpret_cast<uint2*>(d8 + (j0 + j) * dstep) = hq[j];
+                    if (SPLIT == 2) *reinterpret_cast<uint2*>(d8 + (j0 + j) * dstep + a_split) = lq[j];
+                  }
                 }
               }
             } else {
@@ -561,22 +568,27 @@ __device__ __forceinline__ void conv_stream_body(const SParams& p, const CUtenso
               tl_ = t2_;
             }
             if (BC_STREAM_PROD_ILP) {
-              uint2 hq[P_BATCH], lq[P_BATCH];
-              if (snake) {   // snake(0) == 0: padding rows stay zero
 #pragma unroll
-                for (int j = 0; j < P_BATCH; ++j) snake4<SPLIT>(v4[j], sa, sb);
-              }
+              for (int j0 = 0; j0 < P_BATCH; j0 += M_CHUNK) {     // M_CHUNK independent chains at a time
+                uint2 hq[M_CHUNK], lq[M_CHUNK];
+                if (snake) {   // snake(0) == 0: padding rows stay zero
 #pragma unroll
-              for (int j = 0; j < P_BATCH; ++j) split_quad<SPLIT>(v4[j], hq[j], lq[j]);
-#pragma unroll
-              for (int j = 0; j < P_BATCH; ++j) {
-                if (r0 + rstep * j < p.slab_rows) {
-                  uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
-                  *reinterpret_cast<uint2*>(d_) = hq[j];
-                  if (SPLIT == 2) *reinterpret_cast<uint2*>(d_ + a_split) = lq[j];
+                  for (int j = 0; j < M_CHUNK; ++j) if (j0 + j < P_BATCH) snake4<SPLIT>(v4[j0 + j], sa, sb);
                 }
-                ph += ph_step; rr += rr_step;
-                if (ph >= p.stride) { ph -= p.stride; ++rr; }
+#pragma unroll
+                for (int j = 0; j < M_CHUNK; ++j) if (j0 + j < P_BATCH) split_quad<SPLIT>(v4[j0 + j], hq[j], lq[j]);
+#pragma unroll
+                for (int j = 0; j < M_CHUNK; ++j) {
+                  if (j0 + j < P_BATCH) {
+                    if (r0 + rstep * (j0 + j) < p.slab_rows) {
+                      uint8_t* d_ = dst + ((uint32_t)ph * (uint32_t)p.rpp + (uint32_t)rr) * 16u;
+                      *reinterpret_cast<uint2*>(d_) = hq[j];
+                      if (SPLIT == 2) *reinterpret_cast<uint2*>(d_ + a_split) = lq[j];
+                    }
+                    ph += ph_step; rr += rr_step;
+                    if (ph >= p.stride) { ph -= p.stride; ++rr; }
+                  }
+                }
               }
             } else {
 #pragma unroll
