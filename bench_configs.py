@@ -33,20 +33,23 @@ def peaks():
 
 
 def _time(fn, steps, warmup=2):
+    """Median of per-step CUDA-event times (a step that hits a fresh cudaMalloc of the caching allocator would otherwise
+    move a 3-step mean by 10 %)."""
     for _ in range(warmup):
         out = fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         out = fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, out
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+    return ms[len(ms) // 2], out
 
 
 # ----------------------------------------------------------------------------------------------
-def round_trip(model, batch=64, seconds=10.0, steps=3, check=True, enc_sd=None, dec_sd=None, cfg=None):
+def round_trip(model, batch=64, seconds=10.0, steps=5, check=True, enc_sd=None, dec_sd=None, cfg=None):
     """configs[2]: ``BigCodecModel.forward(round_trip=True)`` over the whole batch (the LSTMs run once over it)."""
     from audiotokenization_b200 import synth
     T = int(seconds * 16000)
