@@ -365,6 +365,10 @@ def main():
                 "algorithmic_bytes_per_launch": d_bytes / d_n if d_n else None,
                 "flop_per_launch": d_fl / d_n if d_n else None, "tflops": tflops,
                 "tensor_frac": tflops / peaks["bf16_tflops_sustained"],
+                # the split-precision mode issues three bf16 MMAs per product (hi*hi + hi*lo + lo*hi): the fraction of the tensor
+                # roof its ISSUED arithmetic reaches (informational; `frac` counts the algorithmic FLOPs once, so its ceiling is 1/3)
+                "mma_passes": 3 if args.precision == "bf16x3" else 1,
+                "issued_tensor_frac": (3 if args.precision == "bf16x3" else 1) * tflops / peaks["bf16_tflops_sustained"],
                 "kernel_ms_per_step": d_ms, "share_of_step": d_ms / step_ms if step_ms else None,
                 "all_kernels": {k: kernel_entry(v) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
                 "dense_contractions": {"tflops": conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0,
