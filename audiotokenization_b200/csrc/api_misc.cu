@@ -22,6 +22,7 @@ static Policy read_policy() {
   e = getenv("BC_STREAM_PAIR");  p.stream_pair = (e && e[0] == '0') ? 0 : 1;
   e = getenv("BC_STREAM_TMA");   p.stream_tma = e ? atoi(e) & 3 : 1;     // 0 off, 1 TMA stores, 2 TMA stores + loads
   e = getenv("BC_LSTM_PINGPONG"); p.lstm_pingpong = (e && e[0] == '0') ? 0 : 1;
+  e = getenv("BC_LSTM_COMPACT"); p.lstm_compact = (e && e[0] == '0') ? 0 : 1;  // compact h exchange image for batches below 128 rows
   e = getenv("BC_LSTM_PAIR");    p.lstm_pair = e ? atoi(e) & 3 : 0;            // 1: where one tile per CTA does not fit (measured: no gain over the ping-pong form), 2: whenever the tile count is even
   return p;
 }
@@ -39,8 +40,8 @@ extern "C" int bc_policy(char* buf, size_t n) {
 #else
   const int trace = 0;
 #endif
-  snprintf(buf, n, "tc_variant=%d tc_persist=%d ru_group=%d ru_persist=%d ru_pair=%d stream_pair=%d stream_tma=%d lstm_pingpong=%d lstm_pair=%d trace_build=%d",
-           p.tc_variant, p.tc_persist, p.ru_group, p.ru_persist, p.ru_pair, p.stream_pair, p.stream_tma, p.lstm_pingpong, p.lstm_pair, trace);
+  snprintf(buf, n, "tc_variant=%d tc_persist=%d ru_group=%d ru_persist=%d ru_pair=%d stream_pair=%d stream_tma=%d lstm_pingpong=%d lstm_pair=%d lstm_compact=%d trace_build=%d",
+           p.tc_variant, p.tc_persist, p.ru_group, p.ru_persist, p.ru_pair, p.stream_pair, p.stream_tma, p.lstm_pingpong, p.lstm_pair, p.lstm_compact, trace);
   return BC_OK;
 }
 

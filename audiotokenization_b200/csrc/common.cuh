@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...);
 //   BC_TC_VARIANT (descriptor variant of the per-tile kernel, bring-up only), BC_TC_PERSIST=1, BC_RU_GROUP=0,
 //   BC_RU_PERSIST=0, BC_RU_PAIR=0, BC_STREAM_PAIR=0, BC_LSTM_PINGPONG=0.  None of them changes results; experiments that do are compiled in only with -DBC_TRACE.
 struct Policy {
-  int tc_variant, tc_persist, ru_group, ru_persist, ru_pair, lstm_pingpong, lstm_pair, stream_pair, stream_tma;
+  int tc_variant, tc_persist, ru_group, ru_persist, ru_pair, lstm_pingpong, lstm_pair, lstm_compact, stream_pair, stream_tma;
 };
 const Policy& policy();
 

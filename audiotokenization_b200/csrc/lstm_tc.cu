@@ -49,6 +49,7 @@ struct LstmTcParams {
   unsigned int* counters;  // [m_tiles][CNT_STRIDE]: one step counter per (batch tile, K chunk of h)
   int B, T, H, NS, nslot, n_slices, m_tiles;
   int pre_rows, y_rows;    // rows (time steps) between consecutive batch items of pre / of y and skip (>= T: chunked sequences)
+  int rows;                // rows per 8-channel plane of the exchange image: 128, or round_up(B, 8) for one-tile launches
   int t_base;              // global index of this launch's first step (exchange-buffer parity; > 0: continue from c_state / hx)
   float* c_state;          // [m_tiles * 128][H] cell state carried between the chunks of a sequence (NULL: none)
   uint32_t idesc_wide, idesc_ns;   // N = split*NS (a_hi x [w_hi | w_lo]) and N = NS (a_lo x w_hi)
@@ -99,7 +100,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
 #pragma unroll
   for (int j = 0; j < TPC; ++j) ntile += ((int)blockIdx.y + j * (int)gridDim.y) < p.m_tiles ? 1 : 0;
   const uint32_t w_bytes = (uint32_t)SPLIT * NS * H * 2u;
-  const uint32_t chunk_split = (uint32_t)LM * KC * 2u;           // one chunk of the h tile, one split: 32 KB
+  const uint32_t chunk_split = (uint32_t)LM * KC * 2u;           // one chunk of the h tile, one split: 32 KB (shared-memory stride)
+  // Small batches (one tile, B < 128): the exchange image holds only R = round_up(B, 8) rows per 8-channel plane, planes
+  // R * 16 bytes apart -- in HBM/L2 AND in shared memory (the operand descriptor's plane stride is R * 16).  The MMA still
+  // reads 128 rows per plane; rows >= R alias the following planes (finite values, or stale shared memory past the last
+  // plane) and only feed accumulator rows >= B, which nobody stores.  At B = 1 a step moves 16 KB of h per CTA instead of 256.
+  const uint32_t R = (uint32_t)p.rows;
+  const uint32_t chunk_bytes = R * KC * 2u;                       // bytes one bulk copy moves
   const uint32_t slot_bytes = chunk_split * SPLIT;
   const uint32_t acc_cols = (uint32_t)SPLIT * NS;                // TMEM columns of one tile's accumulator
   uint8_t* sW = smem_raw;
@@ -138,7 +145,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const size_t hx_tile = (size_t)SPLIT * (H / 8) * LM * 8;        // bf16 elements of one m-tile image (all splits)
+  const size_t hx_split = (size_t)(H / 8) * R * 8;                // bf16 elements of one split of an m-tile image
+  const size_t hx_tile = (size_t)SPLIT * hx_split;
   const size_t hx_parity = hx_tile * p.m_tiles;
 
   if (warp == 0) {
@@ -169,11 +177,11 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
             if (c == 0) LTRACE(0);
             const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
             mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
-            mbar_expect_tx(bar_full + 8u * slot, slot_bytes);
+            mbar_expect_tx(bar_full + 8u * slot, chunk_bytes * SPLIT);
 #pragma unroll
             for (int sp = 0; sp < SPLIT; ++sp)
               bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
-                            src + (size_t)sp * (H / 8) * LM * 8 + (size_t)c * (KC / 8) * LM * 8, chunk_split, bar_full + 8u * slot);
+                            src + (size_t)sp * hx_split + (size_t)c * (KC / 8) * R * 8, chunk_bytes, bar_full + 8u * slot);
           }
           LTRACE(1);
         }
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
     // ======================= MMA issuer (warp-uniform loop, elected lane issues) =======================
     {
       mbar_wait(bar_w, 0);
-      const uint32_t a_plane = LM * 16u;
+      const uint32_t a_plane = R * 16u;
       const uint32_t hi_d = desc_hi(128u);
       const uint32_t b_plane = acc_cols * 16u;                      // stride between the two k-planes of a 16-channel group
       const uint32_t w_lo0 = desc_lo(smem_u32(sW), b_plane);
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
       pre_row[j] = p.pre + (size_t)(row_ok[j] ? b : 0) * p.pre_rows * 4 * H + u_glb;
       out_row[j] = (size_t)(row_ok[j] ? b : 0) * p.y_rows * H + u_glb;
       // exchange-buffer position of this thread's units: plane = u_glb / 8, element = u_glb % 8
-      hx_off[j] = (size_t)(j < ntile ? m : 0) * hx_tile + ((size_t)(u_glb >> 3) * LM + row) * 8 + (u_glb & 7);
+      hx_off[j] = (size_t)(j < ntile ? m : 0) * hx_tile + ((size_t)(u_glb >> 3) * R + row) * 8 + (u_glb & 7);
       counter[j] = p.counters + (j < ntile ? m : 0) * CNT_STRIDE + (n * U) / KC;
 #pragma unroll
       for (int u = 0; u < UPW; ++u)
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
         // publish h_t (bf16 hi[/lo]) for the next step's MMA, in the UMMA K-major image -- FIRST: every other CTA of
         // this batch tile waits for it.  The fences below wait for all earlier memory operations of the thread, so
         // nothing else (output store, skip load, next step's pre-activation loads) may be in flight before them.
-        {
+        if ((uint32_t)row < R) {
           __nv_bfloat16* dst = p.hx + (size_t)((p.t_base + t) & 1) * hx_parity + hx_off[j];
           __nv_bfloat16 hi[UPW], lo[UPW];
 #pragma unroll
@@ -306,10 +314,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           }
           if constexpr (UPW == 4) {
             *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hi);
-            if (SPLIT == 2) *reinterpret_cast<uint2*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint2*>(lo);
+            if (SPLIT == 2) *reinterpret_cast<uint2*>(dst + hx_split) = *reinterpret_cast<uint2*>(lo);
           } else {
             *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(hi);
-            if (SPLIT == 2) *reinterpret_cast<uint32_t*>(dst + (size_t)(H / 8) * LM * 8) = *reinterpret_cast<uint32_t*>(lo);
+            if (SPLIT == 2) *reinterpret_cast<uint32_t*>(dst + hx_split) = *reinterpret_cast<uint32_t*>(lo);
           }
         }
         // make the h stores visible: generic -> async proxy per thread, then the CTA barrier orders every gate
@@ -733,6 +741,7 @@ static int lstm_tc_launch(const float* pre, const void* w_image, const float* sk
   p.counters = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(workspace) + hx_pad);
   p.B = B; p.T = T; p.H = H; p.NS = pl.NS; p.nslot = pl.nslot; p.n_slices = pl.n_slices; p.m_tiles = pl.m_tiles;
   p.pre_rows = pre_rows; p.y_rows = y_rows; p.t_base = t_base; p.c_state = c_state;
+  p.rows = (pl.m_tiles == 1 && !pl.pair && bc::policy().lstm_compact) ? ((B + 7) / 8) * 8 : LM;
   p.idesc_wide = bc::tc::idesc_bf16_m128(pl.split * pl.NS);
   p.idesc_ns = bc::tc::idesc_bf16_m128(pl.NS);
   // a new sequence starts from h = 0 (the exchange buffer) and fresh step counters; a continued one keeps h and only

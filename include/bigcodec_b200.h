@@ -65,6 +65,7 @@ const char* bc_last_error(void);
  *   BC_STREAM_PAIR = 0     streamed-weight kernel without the CTA-pair (cta_group::2) form
  *   BC_STREAM_TMA = 0|1|2  plain streamed convs: no tensor maps | y by TMA stores (default) | x boxes by TMA as well
  *   BC_LSTM_PINGPONG = 0   one batch tile per CTA only (max batch 256);  BC_LSTM_PAIR = 1  CTA-pair recurrence kernel
+ *   BC_LSTM_COMPACT = 0    full 128-row h exchange image also for batches below 128 rows
  *   BC_TC_VARIANT / BC_TC_PERSIST   per-tile tcgen05 conv variants (development) */
 int bc_policy(char* buf, size_t n);
 /* 0 if device `dev` exists and is sm_100; fills optional outputs. */

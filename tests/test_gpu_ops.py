@@ -733,3 +733,47 @@ def test_res_lstm_cta_pair_recurrence_is_bit_identical():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("lstm pair ok") == 3, r.stdout
+
+
+_LSTM_COMPACT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {repo!r})
+from audiotokenization_b200 import _cabi, ops
+from audiotokenization_b200.vq import module as M
+assert "lstm_compact=0" in _cabi.policy(), _cabi.policy()
+out = {{}}
+for H, B, T in {cases!r}:
+    g = torch.Generator().manual_seed(H + B + T)
+    torch.manual_seed(H + B + T)                  # the module's random initial weights
+    m = M.ResLSTM(H, num_layers=1).cuda()
+    img = m.lstm.recurrent_image_for(0, "bf16x3")
+    pre = (torch.randn(B, T, 4 * H, generator=g) * 0.7).cuda()
+    skip = torch.randn(B, T, H, generator=g).cuda()
+    out[(H, B, T)] = ops.lstm_recurrent_tc(pre, img, skip, "bf16x3", ops.lstm_tc_max_batch(H, "bf16x3")).cpu()
+torch.save(out, {path!r})
+"""
+
+
+def test_res_lstm_compact_exchange_image_is_bit_identical(tmp_path):
+    """One-tile launches (B < 128) exchange h in a compact image of round_up(B, 8) rows per 8-channel plane (the MMA's rows
+    beyond it alias other planes and only feed accumulator rows nobody stores).  Same arithmetic for the valid rows: the
+    results must equal the full 128-row image (BC_LSTM_COMPACT=0, hence the subprocess) bit for bit."""
+    import os, subprocess, sys
+    from audiotokenization_b200 import _cabi
+    assert "lstm_compact=1" in _cabi.policy()
+    cases = [(512, 1, 30), (512, 5, 17), (512, 64, 40), (256, 100, 12), (128, 127, 9), (512, 8, 3)]
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "full_image.pt")
+    r = subprocess.run([sys.executable, "-c", _LSTM_COMPACT_SCRIPT.format(repo=repo, cases=cases, path=path)],
+                       env=dict(os.environ, BC_LSTM_COMPACT="0"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    want = torch.load(path)
+    for H, B, T in cases:
+        g = gen(H + B + T)
+        torch.manual_seed(H + B + T)
+        m = M.ResLSTM(H, num_layers=1).to(DEV)
+        img = m.lstm.recurrent_image_for(0, "bf16x3")
+        pre = (torch.randn(B, T, 4 * H, generator=g) * 0.7).to(DEV)
+        skip = torch.randn(B, T, H, generator=g).to(DEV)
+        got = ops.lstm_recurrent_tc(pre, img, skip, "bf16x3", ops.lstm_tc_max_batch(H, "bf16x3")).cpu()
+        assert torch.isfinite(got).all() and torch.equal(got, want[(H, B, T)]), (H, B, T)
