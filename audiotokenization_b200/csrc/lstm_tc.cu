@@ -49,6 +49,8 @@ struct LstmTcParams {
   unsigned int* counters;  // [m_tiles][CNT_STRIDE]: one step counter per (batch tile, K chunk of h)
   int B, T, H, NS, nslot, n_slices, m_tiles;
   int pre_rows, y_rows;    // rows (time steps) between consecutive batch items of pre / of y and skip (>= T: chunked sequences)
+  uint32_t split_stride, ring_bytes;   // shared-memory ring: hi -> lo stride inside a slot, bytes reserved for all slots
+  int whole;               // 1: the compact tile image is one streamed piece per split (see the kernel)
   int rows;                // rows per 8-channel plane of the exchange image: 128, or round_up(B, 8) for one-tile launches
   int t_base;              // global index of this launch's first step (exchange-buffer parity; > 0: continue from c_state / hx)
   float* c_state;          // [m_tiles * 128][H] cell state carried between the chunks of a sequence (NULL: none)
@@ -93,14 +95,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, NS = p.NS, U = NS / 4;
-  const int nchunks = H / KC;
+  const int nchunks_cnt = H / KC;                   // step counters per tile (one per 128 channels of h)
+  // `whole` (compact image that fits one ring slot): the tile's image is ONE piece per split -- one poll of all chunk counters,
+  // one bulk copy per split, one barrier -- instead of H / KC chunks with their own poll, copies and barriers
+  const bool whole = p.whole != 0;
+  const int nchunks = whole ? 1 : nchunks_cnt;
   const int n = blockIdx.x;
   // batch tiles of this CTA: blockIdx.y, blockIdx.y + gridDim.y (the second one may not exist)
   int ntile = 0;
 #pragma unroll
   for (int j = 0; j < TPC; ++j) ntile += ((int)blockIdx.y + j * (int)gridDim.y) < p.m_tiles ? 1 : 0;
   const uint32_t w_bytes = (uint32_t)SPLIT * NS * H * 2u;
-  const uint32_t chunk_split = (uint32_t)LM * KC * 2u;           // one chunk of the h tile, one split: 32 KB (shared-memory stride)
+  const uint32_t chunk_split = p.split_stride;                    // shared-memory bytes between the hi and lo images of a ring slot (32 KB; compact image: less)
   // Small batches (one tile, B < 128): the exchange image holds only R = round_up(B, 8) rows per 8-channel plane, planes
   // R * 16 bytes apart -- in HBM/L2 AND in shared memory (the operand descriptor's plane stride is R * 16).  The MMA still
   // reads 128 rows per plane; rows >= R alias the following planes (finite values, or stale shared memory past the last
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
   const uint32_t acc_cols = (uint32_t)SPLIT * NS;                // TMEM columns of one tile's accumulator
   uint8_t* sW = smem_raw;
   uint8_t* sA = sW + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)slot_bytes * p.nslot);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.ring_bytes);
   // bars: full[nslot] | empty[nslot] | acc_full[MAX_TPC] | acc_empty[MAX_TPC] | w_full
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8u * p.nslot, bar_accf = bar0 + 16u * p.nslot,
@@ -163,7 +169,23 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           // the stragglers of the later ones instead of waiting for the slowest of all n-slices
           const __nv_bfloat16* src = p.hx + (size_t)((p.t_base + t + 1) & 1) * hx_parity + (size_t)m * hx_tile;
           for (int c = 0; c < nchunks; ++c, ++cc) {
-            if (t > 0) {
+            if (t > 0 && whole) {
+              // ONE 16-byte acquire load covers the tile's chunk counters (polls one after the other cost an L2 round trip
+              // each, ~1.5 k cycles, even when already satisfied)
+              {
+                const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
+                unsigned int s0, s1, s2, s3, spins = 0;
+                do {
+                  asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3)
+                               : "l"(p.counters + m * CNT_STRIDE) : "memory");
+                  if (nchunks_cnt < 4) s3 = target;
+                  if (nchunks_cnt < 3) s2 = target;
+                  if (nchunks_cnt < 2) s1 = target;
+                  if (++spins > (1u << 26)) __trap();
+                } while (s0 < target || s1 < target || s2 < target || s3 < target);
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+              }
+            } else if (t > 0) {
               const unsigned int target = (unsigned int)t * (unsigned int)(KC / U);
               unsigned int seen;
               unsigned int spins = 0;
@@ -177,11 +199,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
             if (c == 0) LTRACE(0);
             const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
             mbar_wait(bar_empty + 8u * slot, (use & 1u) ^ 1u);
-            mbar_expect_tx(bar_full + 8u * slot, chunk_bytes * SPLIT);
+            const uint32_t piece = whole ? (uint32_t)hx_split * 2u : chunk_bytes;
+            mbar_expect_tx(bar_full + 8u * slot, piece * SPLIT);
 #pragma unroll
             for (int sp = 0; sp < SPLIT; ++sp)
               bulk_g2s_notx(smem_u32(sA) + slot * slot_bytes + sp * chunk_split,
-                            src + (size_t)sp * hx_split + (size_t)c * (KC / 8) * R * 8, chunk_bytes, bar_full + 8u * slot);
+                            src + (size_t)sp * hx_split + (size_t)c * (KC / 8) * R * 8, piece, bar_full + 8u * slot);
           }
           LTRACE(1);
         }
@@ -203,11 +226,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
           mbar_wait(bar_acce + 8u * j, ((uint32_t)t & 1u) ^ 1u);   // gate warps have drained this tile's accumulator of step t-1
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)j * acc_cols;
-          for (int c = 0; c < nchunks; ++c, ++cc) {
+          for (int c = 0; c < nchunks_cnt; ++c) {
+            const bool first_piece = !whole || c == 0, last_piece = !whole || c == nchunks_cnt - 1;
             const uint32_t slot = cc % p.nslot, use = cc / p.nslot;
-            mbar_wait(bar_full + 8u * slot, use & 1u);
-            tc_fence_after();
-            uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes, a_plane);
+            if (first_piece) {
+              mbar_wait(bar_full + 8u * slot, use & 1u);
+              tc_fence_after();
+            }
+            // whole image: the 128-channel blocks of the single piece follow one another (KC / 8 planes each)
+            uint32_t a_lo = desc_lo(smem_u32(sA) + slot * slot_bytes + (whole ? (uint32_t)c * (KC / 8) * a_plane : 0u), a_plane);
             uint32_t b_lo = w_lo0 + (((uint32_t)c * (KC / 16) * 2u * b_plane) >> 4);
             const uint32_t a_g = (2u * a_plane) >> 4, b_g = (2u * b_plane) >> 4;
 #pragma unroll
@@ -216,8 +243,11 @@ __global__ void __launch_bounds__(L_THREADS, 1) lstm_tc_kernel(const LstmTcParam
               else                  mma_bf16_lohi<true>(d, a_lo, b_lo, hi_d, hi_d, p.idesc_wide);
               if (SPLIT == 2) mma_bf16_lohi<true>(d, a_lo + (chunk_split >> 4), b_lo, hi_d, hi_d, p.idesc_ns);   // a_lo * w_hi
             }
-            if (elect_one()) umma_commit(bar_empty + 8u * slot);
-            __syncwarp();
+            if (last_piece) {
+              if (elect_one()) umma_commit(bar_empty + 8u * slot);
+              __syncwarp();
+              ++cc;
+            }
           }
           if (elect_one()) umma_commit(bar_accf + 8u * j);
           __syncwarp();
@@ -671,7 +701,7 @@ bool lstm_tc_plan(int B, int H, int precision, LstmTcPlan* pl) {
   while (nslot > 2 && w + nslot * slot + 1024 > 225 * 1024) --nslot;
   if (w + nslot * slot + 1024 > 225 * 1024) return false;
   pl->nslot = nslot;
-  pl->smem = w + nslot * slot + (2 * nslot + 2 * MAX_TPC + 1) * 8 + 64;
+  pl->smem = w + nslot * slot + (2 * (H / KC > nslot ? H / KC : nslot) + 2 * MAX_TPC + 1) * 8 + 64;   // barriers for up to H / KC slots (compact image)
   pl->hx_bytes = (size_t)2 * pl->m_tiles * pl->split * (H / 8) * LM * 8 * 2;
   pl->ws_bytes = pl->hx_bytes + (size_t)pl->m_tiles * CNT_STRIDE * sizeof(unsigned int) + 256;
   // one batch tile per CTA while the tiles fit side by side (the latency-optimal shape); otherwise two independent
@@ -742,6 +772,16 @@ static int lstm_tc_launch(const float* pre, const void* w_image, const float* sk
   p.B = B; p.T = T; p.H = H; p.NS = pl.NS; p.nslot = pl.nslot; p.n_slices = pl.n_slices; p.m_tiles = pl.m_tiles;
   p.pre_rows = pre_rows; p.y_rows = y_rows; p.t_base = t_base; p.c_state = c_state;
   p.rows = (pl.m_tiles == 1 && !pl.pair && bc::policy().lstm_compact) ? ((B + 7) / 8) * 8 : LM;
+  p.split_stride = (uint32_t)LM * KC * 2u;
+  p.ring_bytes = (uint32_t)pl.nslot * p.split_stride * (uint32_t)pl.split;
+  p.whole = 0;
+  if (p.rows < LM && H / KC <= 4) {
+    // compact image that fits the ring as ONE piece per split: a single slot, hi image then lo image.  The MMA reads 128 rows
+    // per plane whatever R is: 4 KB of the ring stay free behind the images for that over-read.
+    const uint32_t split_bytes = (uint32_t)(H / 8) * (uint32_t)p.rows * 16u;
+    const uint32_t stride_c = (split_bytes + 1023u) & ~1023u;
+    if ((size_t)stride_c * pl.split + 4096 <= p.ring_bytes) { p.split_stride = stride_c; p.nslot = 1; p.whole = 1; }
+  }
   p.idesc_wide = bc::tc::idesc_bf16_m128(pl.split * pl.NS);
   p.idesc_ns = bc::tc::idesc_bf16_m128(pl.NS);
   // a new sequence starts from h = 0 (the exchange buffer) and fresh step counters; a continued one keeps h and only
